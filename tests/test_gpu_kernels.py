@@ -1,0 +1,123 @@
+"""GPU parity of the primitive kernels, called through the C ABI test hooks (include/tevo.h)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def _zgemm(tevo, ta, tb, M, N, K, alpha, A, B, beta, Cm):
+    from timeevomps_jl_b200._lib import load, check, tevo_complex, default_ctx
+    ctx = default_ctx()
+    A = np.asfortranarray(A.astype(np.complex128))
+    B = np.asfortranarray(B.astype(np.complex128))
+    Cm = np.asfortranarray(Cm.astype(np.complex128)).copy(order="F")
+    check(load().tevo_test_zgemm(ctx.h, ta, tb, M, N, K, tevo_complex(alpha.real, alpha.imag), A.ctypes.data,
+                                 A.shape[0], B.ctypes.data, B.shape[0], tevo_complex(beta.real, beta.imag),
+                                 Cm.ctypes.data, Cm.shape[0]), ctx.h)
+    return Cm
+
+
+def _opnp(X, t):
+    return X if t == 0 else (X.T if t == 1 else X.conj().T)
+
+
+@pytest.mark.parametrize("ta", [0, 1, 2])
+@pytest.mark.parametrize("tb", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 4, 2), (7, 5, 3), (33, 65, 17), (128, 64, 16), (130, 70, 50),
+                                   (256, 192, 129), (300, 20, 515)])
+def test_zgemm_matches_numpy(tevo, ta, tb, shape):
+    """DMMA ZGEMM vs numpy complex128; tolerance 1e-13 relative to |A||B| (fp64 accumulation order differs)."""
+    M, N, K = shape
+    rng = np.random.default_rng(M * 1000 + N * 10 + K + ta * 3 + tb)
+    A = _rand(rng, M, K) if ta == 0 else _rand(rng, K, M)
+    B = _rand(rng, K, N) if tb == 0 else _rand(rng, N, K)
+    C0 = _rand(rng, M, N)
+    alpha, beta = 0.7 - 0.3j, -0.2 + 1.1j
+    got = _zgemm(tevo, ta, tb, M, N, K, alpha, A, B, beta, C0)
+    ref = alpha * (_opnp(A, ta) @ _opnp(B, tb)) + beta * C0
+    scale = np.linalg.norm(_opnp(A, ta), axis=1).max() * np.linalg.norm(_opnp(B, tb), axis=0).max() + 1
+    assert np.abs(got - ref).max() <= 1e-13 * scale
+    got0 = _zgemm(tevo, ta, tb, M, N, K, 1.0 + 0j, A, B, 0j, np.full((M, N), np.nan + 0j))
+    assert np.abs(got0 - _opnp(A, ta) @ _opnp(B, tb)).max() <= 1e-13 * scale
+
+
+def _split(tevo, theta, left, normalize=False, **tr):
+    from timeevomps_jl_b200._lib import load, check, tevo_spec, default_ctx, make_trunc
+    ctx = default_ctx()
+    m, n = theta.shape
+    th = np.asfortranarray(theta.astype(np.complex128))
+    k = min(m, n)
+    L = np.zeros((m, k), dtype=np.complex128, order="F")
+    R = np.zeros((k, n), dtype=np.complex128, order="F")
+    eigs = np.zeros(k)
+    spec = tevo_spec()
+    t = make_trunc(**tr)
+    check(load().tevo_test_split(ctx.h, m, n, th.ctypes.data, C.byref(t), 1 if left else 0, 1 if normalize else 0,
+                                 C.byref(spec), eigs.ctypes.data_as(C.POINTER(C.c_double)), k, L.ctypes.data,
+                                 R.ctypes.data, k), ctx.h)
+    kk = spec.nkeep
+    Lf = np.ndarray((m, kk), dtype=np.complex128, buffer=L.data, order="F").copy()
+    Rf = np.ndarray((kk, n), dtype=np.complex128, buffer=R.data, order="F").copy()
+    return Lf, Rf, eigs[:kk].copy(), spec
+
+
+@pytest.mark.parametrize("left", [True, False])
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (4, 2), (2, 4), (8, 8), (20, 20), (64, 32), (32, 64), (96, 96)])
+def test_split_untruncated(tevo, oracle, left, shape):
+    m, n = shape
+    rng = np.random.default_rng(m * 100 + n)
+    th = _rand(rng, m, n)
+    L, R, eigs, spec = _split(tevo, th, left)
+    k = min(m, n)
+    assert spec.nkeep == k and spec.truncerr == 0.0
+    S = np.linalg.svd(th, compute_uv=False)
+    np.testing.assert_allclose(eigs, S ** 2, rtol=1e-11, atol=1e-13 * S[0] ** 2)
+    assert np.abs(L @ R - th).max() <= 1e-12 * S[0]
+    iso = L.conj().T @ L if left else R @ R.conj().T
+    assert np.abs(iso - np.eye(k)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("left", [True, False])
+@pytest.mark.parametrize("tr", [dict(maxdim=7), dict(cutoff=1e-3), dict(maxdim=20, cutoff=1e-6),
+                                dict(cutoff=1e-2, mindim=12), dict(cutoff=0.05, use_absolute_cutoff=True),
+                                dict(maxdim=5, mindim=5)])
+def test_split_truncation_matches_oracle(tevo, oracle, left, tr):
+    """Same bond dimension, truncerr, spectrum, entropy and truncated state as the oracle's replacebond!."""
+    rng = np.random.default_rng(7)
+    m, n = 24, 32
+    # decaying spectrum so that cutoffs bite
+    U, _ = np.linalg.qr(_rand(rng, m, m))
+    V, _ = np.linalg.qr(_rand(rng, n, n))
+    s = np.exp(-0.6 * np.arange(m))
+    th = (U * s) @ V[:m]
+    L, R, eigs, spec = _split(tevo, th, left, normalize=True, **tr)
+    psi = oracle.MPS([np.zeros((m // 2, 2, 1)), np.zeros((1, 2, n // 2))])
+    ospec = psi.replacebond(0, th.reshape(m // 2, 2, 2, n // 2), ortho="left" if left else "right", normalize=True,
+                            **tr)
+    assert spec.nkeep == len(ospec.eigs)
+    np.testing.assert_allclose(eigs, ospec.eigs, rtol=1e-10)
+    assert abs(spec.truncerr - ospec.truncerr) <= 1e-10 * max(ospec.truncerr, 1e-30) + 1e-18
+    assert abs(spec.entropy - ospec.entropy()) <= 1e-10
+    oth = np.tensordot(psi.A[0], psi.A[1], axes=(2, 0)).reshape(m, n)
+    assert np.abs(L @ R - oth).max() <= 1e-12
+    assert abs(np.linalg.norm(L @ R) - 1.0) <= 1e-13
+
+
+def test_split_rank_deficient(tevo):
+    """Exact zero singular values (product-state growth, test/test_tebd.jl:31-33): isometry stays unitary."""
+    rng = np.random.default_rng(3)
+    a, b = _rand(rng, 16, 3), _rand(rng, 3, 16)
+    th = a @ b
+    for left in (True, False):
+        L, R, eigs, spec = _split(tevo, th, left)
+        assert spec.nkeep == 16
+        assert np.abs(L @ R - th).max() <= 1e-12 * np.linalg.norm(th)
+        iso = L.conj().T @ L if left else R @ R.conj().T
+        assert np.abs(iso - np.eye(16)).max() <= 1e-12
+        assert np.all(np.isfinite(L)) and np.all(np.isfinite(R))

@@ -1,0 +1,91 @@
+// Common device/host helpers for libtevo (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace tevo {
+
+typedef double2 cplx;  // (re, im), 16-byte aligned, bit-compatible with C `double _Complex` / Julia ComplexF64
+
+__host__ __device__ inline cplx mk(double re, double im) { return make_double2(re, im); }
+__host__ __device__ inline cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ inline cplx cconj(cplx a) { return mk(a.x, -a.y); }
+__host__ __device__ inline cplx cscale(double s, cplx a) { return mk(s * a.x, s * a.y); }
+__host__ __device__ inline double cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+// a += conj(x) * y
+__host__ __device__ inline void cfma_conj(cplx& a, cplx x, cplx y) {
+  a.x += x.x * y.x + x.y * y.y;
+  a.y += x.x * y.y - x.y * y.x;
+}
+__host__ __device__ inline void cfma(cplx& a, cplx x, cplx y) {
+  a.x += x.x * y.x - x.y * y.y;
+  a.y += x.x * y.y + x.y * y.x;
+}
+
+enum Op { OP_N = 0, OP_T = 1, OP_C = 2 };
+
+// error plumbing: every internal function returns cudaError_t-like int; the C ABI maps to TEVO_* codes
+struct Status {
+  int code = 0;
+  std::string msg;
+};
+
+#define TEVO_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      throw tevo::CudaError(_e, __FILE__, __LINE__);                                           \
+    }                                                                                          \
+  } while (0)
+
+extern long long g_launches;  // kernels launched by the library (all contexts)
+#define TEVO_LAUNCHED()                 \
+  do {                                  \
+    ++tevo::g_launches;                 \
+    TEVO_CUDA_CHECK(cudaGetLastError()); \
+  } while (0)
+
+struct CudaError {
+  cudaError_t err;
+  const char* file;
+  int line;
+  CudaError(cudaError_t e, const char* f, int l) : err(e), file(f), line(l) {}
+};
+
+struct TevoError {
+  int code;
+  std::string msg;
+  TevoError(int c, std::string m) : code(c), msg(std::move(m)) {}
+};
+
+// warp / block reductions (double)
+__device__ inline double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of up to 3 doubles at once; result valid in all threads. blockDim.x multiple of 32, <= 1024
+template <int NV>
+__device__ inline void block_sum(double (&v)[NV], double* smem /* >= NV*32 doubles */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = (lane < nw) ? smem[i * 32 + lane] : 0.0;
+    v[i] = warp_sum(x);
+  }
+}
+
+}  // namespace tevo

@@ -1,0 +1,229 @@
+// Complex-FP64 GEMM on the FP64 tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4), sm_100a.
+//
+// C(MxN, col-major, ldc) = alpha * op(A)(MxK) * op(B)(KxN) + beta * C,   op in {N, T, C}
+//
+// This is the ZGEMM-class workhorse behind theta = A_b * A_{b+1}  (src/bondgate.jl:49-50, src/tdvp.jl:60),
+// the split-back GEMMs of replacebond! (src/bondgate.jl:51, src/tdvp.jl:64), the centre-move products of
+// orthogonalize! (src/bondgate.jl:48) and the L*theta / T*R legs of ProjMPO's product (src/tdvp.jl:61,81).
+//
+// Design: interleaved (re,im) operands are staged by cp.async (16 B = one complex element per copy, zero-fill
+// out of range) through a 3-stage shared-memory ring; one LDS.128 fetches the (re,im) pair a thread needs for
+// an m8n8k4 fragment, so no planar repack is required.  A complex MAC is 4 real DMMAs:
+//   Cre += Are*Bre ; Cre += (-Aim)*Bim ; Cim += Are*Bim ; Cim += Aim*Bre .
+// CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread).
+#include "common.cuh"
+#include "zgemm.h"
+
+namespace tevo {
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, NTHREADS = 256;
+constexpr int KPAD = 4;  // k-contiguous tiles: row stride (BK+4)*16 B = 320 B -> odd multiple of 64 B
+constexpr int MPAD = 2;  // m-contiguous tiles: k stride (ROWS+2)*16 B == 32 B mod 128 B
+
+template <int ROWS, bool KMAJOR>
+struct Tile {
+  static constexpr int elems = KMAJOR ? ROWS * (BK + KPAD) : BK * (ROWS + MPAD);
+  __device__ static inline int idx(int r, int k) { return KMAJOR ? r * (BK + KPAD) + k : k * (ROWS + MPAD) + r; }
+};
+
+__device__ inline void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ inline void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Stage a ROWS x BK tile of an operand.  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
+template <int ROWS, bool KMAJOR>
+__device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, int r0, int k0, int R, int K) {
+  typedef Tile<ROWS, KMAJOR> T;
+#pragma unroll
+  for (int e = threadIdx.x; e < ROWS * BK; e += NTHREADS) {
+    int r, k;
+    if (KMAJOR) {
+      r = e / BK;
+      k = e % BK;
+    } else {
+      k = e / ROWS;
+      r = e % ROWS;
+    }
+    bool p = (r0 + r < R) && (k0 + k < K);
+    const cplx* src = g;
+    if (p) src = KMAJOR ? g + (long)(r0 + r) * ld + (k0 + k) : g + (long)(k0 + k) * ld + (r0 + r);
+    cp_async16(&s[T::idx(r, k)], src, p);
+  }
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+zgemm_dmma_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
+                  const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc) {
+  typedef Tile<BM, A_KMAJOR> TA;
+  typedef Tile<BN, B_KMAJOR> TB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* sA = reinterpret_cast<cplx*>(smem_raw);
+  cplx* sB = sA + STAGES * TA::elems;
+
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int g = lane >> 2, tq = lane & 3;
+
+  double cre[4][4][2], cim[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cre[i][j][0] = cre[i][j][1] = 0.0;
+      cim[i][j][0] = cim[i][j][1] = 0.0;
+    }
+
+  const int nk = (K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<BM, A_KMAJOR>(sA + s * TA::elems, A, lda, m0, s * BK, M, K);
+      load_tile<BN, B_KMAJOR>(sB + s * TB::elems, B, ldb, n0, s * BK, N, K);
+    }
+    cp_async_commit();
+  }
+
+  const double sa = conjA ? -1.0 : 1.0, sb = conjB ? -1.0 : 1.0;
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = kt + STAGES - 1;
+      if (nx < nk) {
+        const int st = nx % STAGES;
+        load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
+        load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
+      }
+      cp_async_commit();
+    }
+    const cplx* a_s = sA + (kt % STAGES) * TA::elems;
+    const cplx* b_s = sB + (kt % STAGES) * TB::elems;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double are[4], aim[4], nai[4], bre[4], bim[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        cplx a = a_s[TA::idx(wm + i * 8 + g, kk + tq)];
+        are[i] = a.x;
+        aim[i] = sa * a.y;
+        nai[i] = -aim[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cplx b = b_s[TB::idx(wn + j * 8 + g, kk + tq)];
+        bre[j] = b.x;
+        bim[j] = sb * b.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], nai[i], bim[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  const bool has_beta = (beta.x != 0.0 || beta.y != 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + wm + i * 8 + g;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n0 + wn + j * 8 + tq * 2 + e;
+        if (col >= N) continue;
+        cplx v = cmul(alpha, mk(cre[i][j][e], cim[i][j][e]));
+        cplx* dst = C + (long)col * ldc + row;
+        if (has_beta) v = cadd(v, cmul(beta, *dst));
+        *dst = v;
+      }
+    }
+  }
+}
+
+template <bool AK, bool BK_>
+void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
+            long ldb, int conjB, cplx beta, cplx* C, long ldc) {
+  typedef Tile<BM, AK> TA;
+  typedef Tile<BN, BK_> TB;
+  const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
+  static bool configured = false;
+  if (!configured) {
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+    configured = true;
+  }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc);
+  TEVO_LAUNCHED();
+}
+
+__global__ void zscale_matrix_kernel(int M, int N, cplx beta, cplx* C, long ldc) {
+  long total = (long)M * N;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    int i = (int)(e % M);
+    long j = e / M;
+    cplx* p = C + j * ldc + i;
+    *p = (beta.x == 0.0 && beta.y == 0.0) ? mk(0, 0) : cmul(beta, *p);
+  }
+}
+
+}  // namespace
+
+long g_zgemm_launches = 0;
+long long g_launches = 0;
+
+void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
+           long ldb, cplx beta, cplx* C, long ldc) {
+  if (M <= 0 || N <= 0) return;
+  ++g_zgemm_launches;
+  if (K <= 0) {
+    long total = (long)M * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    zscale_matrix_kernel<<<blocks, 256, 0, st>>>(M, N, beta, C, ldc);
+    TEVO_LAUNCHED();
+    return;
+  }
+  const bool ak = (ta != OP_N);  // op(A)(i,k) = A[k + i*lda]  -> k contiguous
+  const bool bk = (tb == OP_N);  // op(B)(k,j) = B[k + j*ldb]  -> k contiguous
+  const int ca = (ta == OP_C), cb = (tb == OP_C);
+  if (ak && bk)
+    launch<true, true>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
+  else if (ak && !bk)
+    launch<true, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
+  else if (!ak && bk)
+    launch<false, true>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
+  else
+    launch<false, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
+}
+
+}  // namespace tevo

@@ -1,0 +1,8 @@
+#pragma once
+#include "common.cuh"
+namespace tevo {
+// C = alpha*op(A)*op(B) + beta*C, column-major, complex FP64 on the DMMA pipe.
+void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
+           long ldb, cplx beta, cplx* C, long ldc);
+extern long g_zgemm_launches;
+}  // namespace tevo
