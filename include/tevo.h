@@ -176,6 +176,14 @@ int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* theta, cons
                     int normalize, tevo_spec* spec, double* eigs, int eigs_cap, tevo_complex* L, tevo_complex* R,
                     int kcap);
 
+/* Hermitian eigen-decomposition of a host n x n matrix (full storage, column-major): eigenvalues in descending
+ * order and the matching eigenvectors (columns of U) - the core of the split, exposed for tests */
+int tevo_test_heig(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U);
+
+/* per-phase device timing with CUDA events on the library stream (bench.py's roofline object).  Off by default. */
+int tevo_profile_enable(int on);
+int tevo_profile_read(char* buf, size_t cap, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""CPU-side checks of the drop-in boundary: libtevo.so loads and exports every symbol include/tevo.h declares,
+the ctypes prototypes cover them all, and the product path refuses to run without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "tevo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tevo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(tevo):
+    import __graft_entry__ as g
+    if not os.path.exists(tevo.LIB_PATH):
+        g.build()
+    lib = ctypes.CDLL(tevo.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+
+
+def test_ctypes_prototypes_cover_header(tevo):
+    from timeevomps_jl_b200._lib import PROTOTYPES
+    assert sorted(PROTOTYPES) == _header_symbols()
+
+
+def test_no_torch_or_cpp_types_in_abi():
+    src = open(os.path.join(ROOT, "include", "tevo.h")).read()
+    assert "torch" not in src and "std::" not in src and "at::" not in src
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "timeevomps.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                assert "oracle" not in open(os.path.join(dp, f)).read().replace("# oracle-free", ""), f
+
+
+def test_fails_loudly_without_gpu(tevo):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(tevo.TevoError) as ei:
+        tevo.MPS.product([0, 0, 0, 0])
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_host_side_gate_construction_matches_oracle(tevo, oracle):
+    """BondOperator/gates/exp/time_evo_gates are host code on both sides; the product uses its own expm."""
+    import numpy as np
+    N = 9
+    for (hp, ho) in ((tevo.tfi_bondop(N, 1.0, 0.5), oracle.tfi_bondop(N, 1.0, 0.5)),
+                     (tevo.xxz_bondop(N, 0.7, 0.3), oracle.xxz_bondop(N, 0.7, 0.3))):
+        gp, go = tevo.gates(hp), ho.gates()
+        for a, b in zip(gp, go):
+            assert a.b == b.b and np.array_equal(a.G, b.G)
+        for alg_p, alg_o in ((tevo.TEBD2(), oracle.TEBD2()), (tevo.TEBD4(), oracle.TEBD4()),
+                             (tevo.TEBD2Sweep(), oracle.TEBD2Sweep())):
+            for dt in (0.05, -0.1j):
+                P = tevo.time_evo_gates(dt, gp, alg_p)
+                O = oracle.time_evo_gates(dt, go, alg_o)
+                for Lp, Lo in zip(P, O):
+                    assert len(Lp) == len(Lo)
+                    for layer_p, layer_o in zip(Lp, Lo):
+                        assert [g.b for g in layer_p] == [g.b for g in layer_o]
+                        for a, b in zip(layer_p, layer_o):
+                            assert np.abs(a.G - b.G).max() < 1e-14
+
+
+def test_callback_gating_host_logic(tevo):
+    """test/test_callbacks.jl:21-24 gating without touching the device."""
+    cb = tevo.LocalMeasurementCallback(["Sz", "Sx"], 10, 0.1)
+    assert cb.callback_dt() == 0.1 and len(tevo.measurement_ts(cb)) == 0
+    assert not cb.wants(0.03, True, 0, tevo.TEBD2())
+    assert not cb.wants(0.1, False, 0, tevo.TEBD2())
+    assert cb.wants(0.1, True, 2, tevo.TEBD2())
+    assert not cb.wants(0.1, True, 1, tevo.TEBD2())      # even (1-based) bond filtered for TEBD (callback.jl:84)
+    assert cb.wants(0.1, True, 1, tevo.TDVP2())
+    nb = tevo.NoTEvoCallback()
+    assert nb.apply(None, t=0, bond=1, sweepend=True) is None and nb.checkdone(None) is False
+    assert nb.callback_dt() == 0
+    with pytest.raises(ValueError):
+        tevo.SpecCallback(0.1, 10, bonds=[0, 9])

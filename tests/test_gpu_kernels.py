@@ -121,3 +121,53 @@ def test_split_rank_deficient(tevo):
         iso = L.conj().T @ L if left else R @ R.conj().T
         assert np.abs(iso - np.eye(16)).max() <= 1e-12
         assert np.all(np.isfinite(L)) and np.all(np.isfinite(R))
+
+
+def _heig(tevo, A):
+    from timeevomps_jl_b200._lib import load, check, default_ctx
+    ctx = default_ctx()
+    n = A.shape[0]
+    Af = np.asfortranarray(A.astype(np.complex128))
+    w = np.zeros(n)
+    U = np.zeros((n, n), dtype=np.complex128, order="F")
+    check(load().tevo_test_heig(ctx.h, n, Af.ctypes.data, w.ctypes.data_as(C.POINTER(C.c_double)), U.ctypes.data),
+          ctx.h)
+    return w, U
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 16, 31, 32, 33, 64, 65, 100, 129, 200, 257, 512])
+def test_heig_random_hermitian(tevo, n):
+    """tridiagonalisation + divide&conquer + back-transformation vs numpy.linalg.eigh"""
+    rng = np.random.default_rng(n)
+    X = _rand(rng, n, n)
+    A = X + X.conj().T
+    w, U = _heig(tevo, A)
+    wr = np.linalg.eigvalsh(A)[::-1]
+    nrm = np.abs(wr).max()
+    assert np.abs(w - wr).max() <= 1e-13 * nrm * max(1, n ** 0.5)
+    assert np.abs(U.conj().T @ U - np.eye(n)).max() <= 1e-13 * max(1, n ** 0.5)
+    assert np.abs(A @ U - U * w).max() <= 1e-13 * nrm * max(1, n)
+
+
+@pytest.mark.parametrize("kind", ["lowrank", "graded", "clustered", "zero", "identity"])
+def test_heig_hard_spectra(tevo, kind):
+    rng = np.random.default_rng(11)
+    n = 160
+    Q, _ = np.linalg.qr(_rand(rng, n, n))
+    if kind == "lowrank":
+        s = np.concatenate([rng.random(9) + 0.5, np.zeros(n - 9)])
+    elif kind == "graded":
+        s = 10.0 ** (-np.arange(n) / 8.0)
+    elif kind == "clustered":
+        s = np.concatenate([np.ones(50), 0.5 * np.ones(50) * (1 + 1e-13 * rng.random(50)), 1e-3 * np.ones(60)])
+    elif kind == "zero":
+        s = np.zeros(n)
+    else:
+        s = np.ones(n)
+    A = (Q * s) @ Q.conj().T
+    A = 0.5 * (A + A.conj().T)
+    w, U = _heig(tevo, A)
+    nrm = max(np.abs(s).max(), 1e-300)
+    assert np.abs(np.sort(w) - np.sort(s)).max() <= 1e-13 * nrm * n ** 0.5 + 1e-300
+    assert np.abs(U.conj().T @ U - np.eye(n)).max() <= 2e-13 * n ** 0.5
+    assert np.abs(A @ U - U * w).max() <= 1e-13 * nrm * n + 1e-300

@@ -41,10 +41,10 @@ def test_orthogonalize_preserves_state(tevo, oracle):
         ts = p.tensors()
         for i in range(j):
             A = ts[i].reshape(-1, ts[i].shape[2])
-            assert np.abs(A.conj().T @ A - np.eye(A.shape[1])).max() < 1e-12
+            assert np.abs(A.conj().T @ A - np.eye(A.shape[1])).max() < 1e-10  # Gram-route centre move: ~eps*cond^2
         for i in range(j + 1, 7):
             A = ts[i].reshape(ts[i].shape[0], -1)
-            assert np.abs(A @ A.conj().T - np.eye(A.shape[0])).max() < 1e-12
+            assert np.abs(A @ A.conj().T - np.eye(A.shape[0])).max() < 1e-10
 
 
 @pytest.mark.parametrize("ortho", ["left", "right"])

@@ -6,7 +6,7 @@ Host-side mirror of the reference's public interface (names follow src/*.jl; `!`
     TEvoCallback, NoTEvoCallback, LocalMeasurementCallback, SpecCallback, measurement_ts, measurements,
     tfi_mpo, tfi_bondop (test helpers of src/testutils.jl)
 All arithmetic runs in libtevo.so (hand-written sm_100a CUDA, include/tevo.h); there is no CPU fallback."""
-from ._lib import Context, TevoError, default_ctx, load, LIB_PATH
+from ._lib import Context, TevoError, default_ctx, load, LIB_PATH, profile_enable, profile_read
 from .mps import MPS, MPO, Spectrum, inner, inner_mpo, op, tfi_mpo, xxz_mpo
 from .bondop import (BondOperator, BondGate, SiteTerm, BondTerm, GateList, add, bond, bondgate, gates, siteterms,
                      bondterms, coeff, exp, expm, measure, tfi_bondop, xxz_bondop)

@@ -89,6 +89,9 @@ PROTOTYPES = {
     "tevo_test_zgemm": (_I, [_P, _I, _I, _I, _I, _I, tevo_complex, _CP, _I, _CP, _I, tevo_complex, _CP, _I]),
     "tevo_test_split": (_I, [_P, _I, _I, _CP, C.POINTER(tevo_trunc), _I, _I, C.POINTER(tevo_spec), _DP, _I, _CP, _CP,
                              _I]),
+    "tevo_test_heig": (_I, [_P, _I, _CP, _DP, _CP]),
+    "tevo_profile_enable": (_I, [_I]),
+    "tevo_profile_read": (_I, [C.c_char_p, C.c_size_t, _I]),
 }
 
 _lib = None
@@ -171,3 +174,16 @@ def make_trunc(maxdim=None, mindim=None, cutoff=None, use_absolute_cutoff=False,
     t.use_absolute_cutoff = 1 if use_absolute_cutoff else 0
     t.do_rel_cutoff = 1 if do_rel_cutoff else 0
     return t
+
+
+def profile_enable(on: bool = True):
+    load().tevo_profile_enable(1 if on else 0)
+
+
+def profile_read(reset: bool = True) -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    st = load().tevo_profile_read(buf, len(buf), 1 if reset else 0)
+    if st != TEVO_OK:
+        raise TevoError(st, "tevo_profile_read failed")
+    return json.loads(buf.value.decode())

@@ -1,0 +1,518 @@
+// Hermitian eigensolver on the device: blocked Householder tridiagonalisation (persistent cooperative panel kernel +
+// DMMA rank-2k trailing updates), tridiagonal divide & conquer (stedc.cu) and compact-WY back-transformation.
+// It is the core of the truncated split (replacebond!, src/bondgate.jl:51, src/tdvp.jl:64): the density matrix
+// rho = theta theta^+ (or theta^+ theta) is diagonalised and the isometry is read off its leading eigenvectors.
+#include "heig.h"
+
+#include <algorithm>
+
+#include "prof.h"
+#include "zgemm.h"
+
+namespace tevo {
+namespace {
+
+constexpr int PW = 64;  // panel width
+constexpr int RS = 16;  // rows per strip
+constexpr int NT = 256;
+
+struct PanelArgs {
+  int n, p0, pw;
+  cplx* A;
+  long lda;
+  cplx* P;  // n x 2*PW : [V | W]
+  cplx* Q;  // n x 2*PW : [W | V]
+  cplx* Y;  // n x PW   : raw y = A22 v
+  long ldp;
+  double* acc_norm;  // PW
+  double* acc_yv;    // 2*PW
+  double* acc_cw;    // 2*PW*PW
+  double* acc_cv;    // 2*PW*PW   (kept: V^H v, the strictly upper part of V^H V for the compact-WY T factor)
+  unsigned* bar;     // grid barrier counter (zeroed before the launch)
+  double* d;
+  double* e;
+  cplx* taus;
+};
+
+__device__ inline cplx ldcg_c(const cplx* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+// grid-wide barrier for the co-resident (cooperatively launched) panel kernel: one arrival per CTA on a
+// monotonically increasing counter.  Data produced by other CTAs is read with ld.cg afterwards.
+__device__ inline void grid_bar(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum over the 16 "column lanes" (cl = tid/16) for each of the 16 rows (rr = tid%16); valid on cl == 0 threads
+__device__ inline void reduce_cl2(cplx& v0, cplx& v1, cplx* sred) {
+  __syncthreads();
+  sred[threadIdx.x] = v0;
+  sred[NT + threadIdx.x] = v1;
+  __syncthreads();
+  if (threadIdx.x < RS) {
+    cplx s0 = mk(0, 0), s1 = mk(0, 0);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      s0 = cadd(s0, sred[c * RS + threadIdx.x]);
+      s1 = cadd(s1, sred[NT + c * RS + threadIdx.x]);
+    }
+    v0 = s0;
+    v1 = s1;
+  }
+}
+__device__ inline cplx reduce_cl(cplx v, cplx* sred) {
+  __syncthreads();
+  sred[threadIdx.x] = v;
+  __syncthreads();
+  cplx s = mk(0, 0);
+  if (threadIdx.x < RS) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = cadd(s, sred[c * RS + threadIdx.x]);
+  }
+  return s;
+}
+
+// One panel (pw <= 64 columns) of the blocked Householder tridiagonalisation (zlatrd, lower), persistent over its
+// columns with two grid barriers per column.  CTA b owns the 16-row strips s = b, b+G, ... of the trailing rows.
+//   phase A(i): finalise w_{i-1} on the own rows (scalars from the reductions of column i-1), bring column c = p0+i
+//               up to date, accumulate |x|^2                                                        -> barrier
+//   phase B(i): reflector (beta, tau, v), y = A22 v for the own rows (HEMV over full rows, L2-resident), panel
+//               dots W^H v, V^H v and y^H v (w^H v follows algebraically, so w needs no third reduction) -> barrier
+__global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx* sv = reinterpret_cast<cplx*>(smraw);  // v (n - p0 entries max)
+  __shared__ cplx sred[2 * NT];
+  __shared__ cplx pivV[PW], pivW[PW], scw[PW], scv[PW];
+  __shared__ cplx s_tau_prev, s_alpha_prev;
+  __shared__ double sblk[64];
+  const int n = a.n, p0 = a.p0, pw = a.pw;
+  const int tid = threadIdx.x, rr = tid % RS, cl = tid / RS;
+  const int nstrips = (n - p0 + RS - 1) / RS;
+  cplx* Vp = a.P;
+  cplx* Wp = a.P + (long)PW * a.ldp;
+  cplx* Yp = a.Y;
+  unsigned epoch = 0;
+  cplx tau_cur = mk(0, 0);
+
+  for (int i = 0; i <= pw; ++i) {
+    const int c = p0 + i;
+    // ---------------- phase A ----------------
+    // scalars of column i-1
+    if (i > 0) {
+      const int ip = i - 1;
+      for (int k = tid; k < ip; k += NT) {
+        scw[k] = mk(__ldcg(&a.acc_cw[2 * (ip * PW + k)]), __ldcg(&a.acc_cw[2 * (ip * PW + k) + 1]));
+        scv[k] = mk(__ldcg(&a.acc_cv[2 * (ip * PW + k)]), __ldcg(&a.acc_cv[2 * (ip * PW + k) + 1]));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double re = 0.0;
+        for (int k = 0; k < ip; ++k) re += scw[k].x * scv[k].x + scw[k].y * scv[k].y;  // Re(cw^H cv)
+        const cplx yv = mk(__ldcg(&a.acc_yv[2 * ip]) - 2.0 * re, __ldcg(&a.acc_yv[2 * ip + 1]));
+        const cplx wv = cmul(cconj(tau_cur), yv);  // w^H v = conj(tau) (y^H v - 2 Re(cw^H cv))
+        s_tau_prev = tau_cur;
+        s_alpha_prev = cscale(-0.5, cmul(tau_cur, wv));
+      }
+      __syncthreads();
+    }
+    if (i == pw) {
+      // last pass: only finalise w_{pw-1} on the own rows, then leave the column loop
+      const int ip = pw - 1;
+      const int cp = p0 + ip;
+      const cplx taup = s_tau_prev, alphap = s_alpha_prev;
+      for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+        const int r = p0 + s * RS + rr;
+        const bool act = (r < n) && (r >= cp + 1);
+        cplx acc = mk(0, 0);
+        if (act) {
+          for (int k = cl; k < ip; k += 16) {
+            cfma(acc, Vp[(long)k * a.ldp + r], scw[k]);
+            cfma(acc, Wp[(long)k * a.ldp + r], scv[k]);
+          }
+        }
+        const cplx tot = reduce_cl(acc, sred);
+        if (cl == 0 && act) {
+          const cplx y = Yp[(long)ip * a.ldp + r];
+          const cplx v = Vp[(long)ip * a.ldp + r];
+          Wp[(long)ip * a.ldp + r] = cadd(cmul(taup, csub(y, tot)), cmul(alphap, v));
+        }
+      }
+      break;
+    }
+    // pivot row c of V and W (columns k < i); the newest column k = i-1 of W is rebuilt from its raw y
+    for (int k = tid; k < i; k += NT) {
+      pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
+      if (k < i - 1) pivW[k] = ldcg_c(&Wp[(long)k * a.ldp + c]);
+    }
+    __syncthreads();
+    if (i > 0 && tid == 0) {
+      const int ip = i - 1;
+      cplx acc = mk(0, 0);
+      for (int k = 0; k < ip; ++k) {
+        cfma(acc, pivV[k], scw[k]);
+        cfma(acc, pivW[k], scv[k]);
+      }
+      const cplx y = ldcg_c(&Yp[(long)ip * a.ldp + c]);
+      pivW[ip] = cadd(cmul(s_tau_prev, csub(y, acc)), cmul(s_alpha_prev, pivV[ip]));
+    }
+    __syncthreads();
+    double nrm = 0.0;
+    {
+      const int ip = i - 1;
+      const cplx taup = s_tau_prev, alphap = s_alpha_prev;
+      for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+        const int r = p0 + s * RS + rr;
+        const bool act = (r < n) && (r >= c);
+        cplx acc1 = mk(0, 0), acc2 = mk(0, 0);
+        if (act && i > 0) {
+          for (int k = cl; k < ip; k += 16) {
+            const cplx v = Vp[(long)k * a.ldp + r];
+            const cplx w = Wp[(long)k * a.ldp + r];
+            cfma(acc1, v, scw[k]);
+            cfma(acc1, w, scv[k]);
+            cfma(acc2, v, cconj(pivW[k]));
+            cfma(acc2, w, cconj(pivV[k]));
+          }
+        }
+        if (i > 0) reduce_cl2(acc1, acc2, sred);
+        if (cl == 0 && act) {
+          cplx av = a.A[(long)c * a.lda + r];
+          if (i > 0) {
+            const cplx y = Yp[(long)ip * a.ldp + r];
+            const cplx v = Vp[(long)ip * a.ldp + r];
+            const cplx wf = cadd(cmul(taup, csub(y, acc1)), cmul(alphap, v));
+            Wp[(long)ip * a.ldp + r] = wf;
+            cfma(acc2, v, cconj(pivW[ip]));
+            cfma(acc2, wf, cconj(pivV[ip]));
+            av = csub(av, acc2);
+            a.A[(long)c * a.lda + r] = av;
+          }
+          if (r >= c + 2) nrm += cabs2(av);
+        }
+      }
+    }
+    {
+      double v1[1] = {nrm};
+      block_sum<1>(v1, sblk);
+      if (tid == 0 && v1[0] != 0.0) atomicAdd(&a.acc_norm[i], v1[0]);
+    }
+    epoch += gridDim.x;
+    grid_bar(a.bar, epoch);
+    // ---------------- phase B: reflector, v, y = A22 v, panel dots ----------------
+    const double xn2 = __ldcg(&a.acc_norm[i]);
+    const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
+    double beta;
+    cplx tau, scal;
+    if (xn2 == 0.0 && alpha.y == 0.0) {
+      beta = alpha.x;
+      tau = mk(0, 0);
+      scal = mk(0, 0);
+    } else {
+      beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
+      tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+      const cplx den = mk(alpha.x - beta, alpha.y);
+      const double dn = cabs2(den);
+      scal = mk(den.x / dn, -den.y / dn);
+    }
+    tau_cur = tau;
+    if (blockIdx.x == 0 && tid == 0) {
+      a.d[c] = ldcg_c(&a.A[(long)c * a.lda + c]).x;
+      a.e[c] = beta;
+      a.taus[c] = tau;
+    }
+    const int nv = n - (c + 1);
+    for (int j = tid; j < nv; j += NT) sv[j] = (j == 0) ? mk(1, 0) : cmul(ldcg_c(&a.A[(long)c * a.lda + c + 1 + j]), scal);
+    __syncthreads();
+    cplx cwa[PW / 16], cva[PW / 16];
+#pragma unroll
+    for (int q = 0; q < PW / 16; ++q) cwa[q] = cva[q] = mk(0, 0);
+    double yv0 = 0.0, yv1 = 0.0;
+    for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+      const int r = p0 + s * RS + rr;
+      const bool act = (r < n) && (r >= c + 1);
+      cplx acc = mk(0, 0);
+      if (act) {
+        const cplx* arow = a.A + r;
+        // 8 independent 16-byte loads in flight per thread (the HEMV is latency/L2-bandwidth bound)
+        cplx ac[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) ac[u] = mk(0, 0);
+        int j = c + 1 + cl;
+        for (; j + 16 * 7 < n; j += 16 * 8) {
+          cplx av[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cfma(ac[u], av[u], sv[j + 16 * u - c - 1]);
+        }
+        for (; j < n; j += 16) cfma(ac[0], arow[(long)j * a.lda], sv[j - c - 1]);
+#pragma unroll
+        for (int u = 1; u < 8; ++u) ac[0] = cadd(ac[0], ac[u]);
+        acc = ac[0];
+        const cplx vr = sv[r - c - 1];
+#pragma unroll
+        for (int q = 0; q < PW / 16; ++q) {
+          const int k = cl + 16 * q;
+          if (k < i) {
+            cfma_conj(cwa[q], Wp[(long)k * a.ldp + r], vr);
+            cfma_conj(cva[q], Vp[(long)k * a.ldp + r], vr);
+          }
+        }
+      }
+      const cplx y = reduce_cl(acc, sred);
+      if (cl == 0 && act) {
+        const cplx vr = sv[r - c - 1];
+        Vp[(long)i * a.ldp + r] = vr;
+        Yp[(long)i * a.ldp + r] = y;
+        yv0 += y.x * vr.x + y.y * vr.y;
+        yv1 += y.x * vr.y - y.y * vr.x;
+      }
+    }
+    // reduce the panel dots over the 16 rows of the half-warp, then one atomic per (k, CTA)
+#pragma unroll
+    for (int q = 0; q < PW / 16; ++q) {
+      double x0 = cwa[q].x, x1 = cwa[q].y, x2 = cva[q].x, x3 = cva[q].y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        x0 += __shfl_xor_sync(0xffffffffu, x0, o);
+        x1 += __shfl_xor_sync(0xffffffffu, x1, o);
+        x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+        x3 += __shfl_xor_sync(0xffffffffu, x3, o);
+      }
+      const int k = cl + 16 * q;
+      if (rr == 0 && k < i) {
+        atomicAdd(&a.acc_cw[2 * (i * PW + k)], x0);
+        atomicAdd(&a.acc_cw[2 * (i * PW + k) + 1], x1);
+        atomicAdd(&a.acc_cv[2 * (i * PW + k)], x2);
+        atomicAdd(&a.acc_cv[2 * (i * PW + k) + 1], x3);
+      }
+    }
+    {
+      double v2[2] = {yv0, yv1};
+      block_sum<2>(v2, sblk);
+      if (tid == 0) {
+        atomicAdd(&a.acc_yv[2 * i], v2[0]);
+        atomicAdd(&a.acc_yv[2 * i + 1], v2[1]);
+      }
+    }
+    epoch += gridDim.x;
+    grid_bar(a.bar, epoch);
+  }
+  // ---------------- panel epilogue: build [V|W], [W|V], store reflectors into A ----------------
+  __syncthreads();
+  for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+    for (int k = cl; k < pw; k += 16) {
+      const int r = p0 + s * RS + rr;
+      if (r >= n) continue;
+      const int c = p0 + k;
+      const cplx v = (r <= c) ? mk(0, 0) : Vp[(long)k * a.ldp + r];
+      const cplx w = (r <= c) ? mk(0, 0) : Wp[(long)k * a.ldp + r];
+      Vp[(long)k * a.ldp + r] = v;
+      Wp[(long)k * a.ldp + r] = w;
+      a.Q[(long)k * a.ldp + r] = w;
+      a.Q[(long)(PW + k) * a.ldp + r] = v;
+      a.A[(long)c * a.lda + r] = v;
+    }
+  }
+  // rows above the panel: explicit zeros in the reflector columns
+  for (long e = (long)blockIdx.x * NT + tid; e < (long)p0 * pw; e += (long)gridDim.x * NT) {
+    const int r = (int)(e % p0);
+    const int k = (int)(e / p0);
+    a.A[(long)(p0 + k) * a.lda + r] = mk(0, 0);
+  }
+}
+
+// compact-WY T factor of one panel: T(j,j) = tau_j ; T(0:j, j) = -tau_j T(0:j,0:j) (V^H v_j)   (zlarft, forward/columnwise)
+__global__ void build_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ acc_cv,
+                               cplx* __restrict__ T /* PW x PW col-major */) {
+  extern __shared__ __align__(16) unsigned char smT[];
+  cplx(*sT)[PW + 1] = reinterpret_cast<cplx(*)[PW + 1]>(smT);
+  const int k = threadIdx.x;  // row
+  cplx(*sS)[PW + 1] = sT + PW;  // S(l, j) = (V^H v_j)_l
+  for (int j = 0; j < PW; ++j)
+    if (k < PW) {
+      sT[k][j] = mk(0, 0);
+      sS[k][j] = (k < j && j < pw) ? mk(acc_cv[2 * (j * PW + k)], acc_cv[2 * (j * PW + k) + 1]) : mk(0, 0);
+    }
+  __syncthreads();
+  for (int j = 0; j < pw; ++j) {
+    const cplx tj = taus[j];
+    cplx val = mk(0, 0);
+    if (k < j) {
+      cplx acc = mk(0, 0);
+      for (int l = k; l < j; ++l) cfma(acc, sT[k][l], sS[l][j]);
+      val = cscale(-1.0, cmul(tj, acc));
+    } else if (k == j) {
+      val = tj;
+    }
+    __syncthreads();
+    if (k < PW) sT[k][j] = val;
+    __syncthreads();
+  }
+  for (int j = 0; j < PW; ++j)
+    if (k < PW) T[(long)j * PW + k] = sT[k][j];
+}
+
+__global__ void last_diag_kernel(int n, cplx* A, long lda, double* d) {
+  d[n - 1] = A[(long)(n - 1) * lda + n - 1].x;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) A[(long)(n - 1) * lda + r] = mk(0, 0);
+}
+
+// U0(:, i) = Z(:, perm[i])  (real -> complex)
+__global__ void gather_real_cols_kernel(int n, int k, const double* __restrict__ Z, long ldz, const int* __restrict__ perm,
+                                        cplx* __restrict__ U, long ldu) {
+  const long total = (long)n * k;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(e % n);
+    const int i = (int)(e / n);
+    U[(long)i * ldu + r] = mk(Z[(long)perm[i] * ldz + r], 0.0);
+  }
+}
+
+}  // namespace
+
+void Heig::init() {
+  int dev = 0;
+  TEVO_CUDA_CHECK(cudaGetDevice(&dev));
+  TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
+  TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (PW + 2 * PW + 4 * PW * PW + 8)));
+  TEVO_CUDA_CHECK(cudaMalloc(&Tblk_, sizeof(cplx) * PW * PW));
+}
+
+void Heig::destroy() {
+  stedc_.destroy();
+  auto fr = [](void* p) {
+    if (p) cudaFree(p);
+  };
+  fr(P_); fr(Q_); fr(Y_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
+  Y_ = nullptr;
+  P_ = Q_ = VT_ = nullptr;
+  d_ = e_ = evals_ = Z_ = acc_ = nullptr;
+  taus_ = Tblk_ = X_ = part_ = nullptr;
+  cap_ = 0;
+}
+
+void Heig::ensure(int n) {
+  if (n <= cap_) return;
+  auto fr = [](void* p) {
+    if (p) cudaFree(p);
+  };
+  fr(P_); fr(Q_); fr(Y_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
+  const size_t nn = (size_t)n * n;
+  TEVO_CUDA_CHECK(cudaMalloc(&P_, sizeof(cplx) * (size_t)n * 2 * PW));
+  TEVO_CUDA_CHECK(cudaMalloc(&Q_, sizeof(cplx) * (size_t)n * 2 * PW));
+  TEVO_CUDA_CHECK(cudaMalloc(&Y_, sizeof(cplx) * (size_t)n * PW));
+  TEVO_CUDA_CHECK(cudaMalloc(&VT_, sizeof(cplx) * nn));
+  TEVO_CUDA_CHECK(cudaMalloc(&d_, sizeof(double) * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&e_, sizeof(double) * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&evals_, sizeof(double) * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&Z_, sizeof(double) * nn));
+  TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * n));
+  xcap_ = n;
+  cap_ = n;
+}
+
+void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
+  if (n < 1) throw TevoError(1, "heig: empty matrix");
+  ensure(n);
+  n_ = n;
+  A_ = A;
+  lda_ = lda;
+  static bool configured = false;
+  if (!configured) {
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(build_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * sizeof(cplx) * PW * (PW + 1))));
+    configured = true;
+  }
+  if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
+  double* acc_norm = acc_;
+  double* acc_yv = acc_ + PW;
+  double* acc_cw = acc_ + 3 * PW;
+  double* acc_cv = acc_ + 3 * PW + 2 * PW * PW;
+  const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
+  int p0 = 0;
+  while (p0 < n - 1) {
+    const int pw = std::min(PW, n - 1 - p0);
+    TEVO_CUDA_CHECK(cudaMemsetAsync(acc_, 0, sizeof(double) * (PW + 2 * PW + 4 * PW * PW + 8), st));
+    PanelArgs pa;
+    pa.n = n; pa.p0 = p0; pa.pw = pw; pa.A = A; pa.lda = lda; pa.P = P_; pa.Q = Q_; pa.Y = Y_; pa.ldp = n;
+    pa.acc_norm = acc_norm; pa.acc_yv = acc_yv; pa.acc_cw = acc_cw; pa.acc_cv = acc_cv;
+    pa.bar = reinterpret_cast<unsigned*>(acc_ + PW + 2 * PW + 4 * PW * PW);
+    pa.d = d_; pa.e = e_; pa.taus = taus_;
+    const int nstrips = (n - p0 + RS - 1) / RS;
+    const int grid = std::max(1, std::min(num_sms_, nstrips));
+    void* args[] = {&pa};
+    const size_t smem = (size_t)(n - p0) * sizeof(cplx);
+    {
+      ProfScope ps(st, P_TRI_PANEL);
+      TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)tridiag_panel_kernel, dim3(grid), dim3(NT), args, smem, st));
+      TEVO_LAUNCHED();
+    }
+    // compact-WY factor and V*T for the back-transformation
+    {
+      ProfScope ps(st, P_TRI_WY);
+      build_T_kernel<<<1, PW, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(pw, taus_ + p0, acc_cv, Tblk_);
+      TEVO_LAUNCHED();
+      zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
+    }
+    const int q0 = p0 + pw;
+    // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H
+    ProfScope ps2(st, P_TRI_HER2K);
+    if (pw == PW) {
+      zgemm(st, OP_N, OP_C, n - q0, n - q0, 2 * PW, MONE, P_ + q0, n, Q_ + q0, n, ONE, A + (long)q0 * lda + q0, lda);
+    } else {
+      zgemm(st, OP_N, OP_C, n - q0, n - q0, pw, MONE, P_ + q0, n, Q_ + q0, n, ONE, A + (long)q0 * lda + q0, lda);
+      zgemm(st, OP_N, OP_C, n - q0, n - q0, pw, MONE, P_ + (long)PW * n + q0, n, Q_ + (long)PW * n + q0, n, ONE,
+            A + (long)q0 * lda + q0, lda);
+    }
+    p0 = q0;
+  }
+  last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
+  TEVO_LAUNCHED();
+  {
+    ProfScope ps(st, P_STEDC);
+    stedc_.run(st, n, d_, e_, evals_, Z_);
+  }
+}
+
+void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ldu) {
+  const int n = n_;
+  if (k < 1) return;
+  ProfScope ps(st, P_BACK);
+  const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
+  {
+    const long total = (long)n * k;
+    int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+    gather_real_cols_kernel<<<blocks, 256, 0, st>>>(n, k, Z_, n, perm_dev, U, ldu);
+    TEVO_LAUNCHED();
+  }
+  if (n < 2) return;
+  if ((size_t)k > xcap_) {
+    if (X_) cudaFree(X_);
+    X_ = nullptr;
+    TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * k));
+    xcap_ = k;
+  }
+  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= (V T) (V^H U)
+  int last = ((n - 2) / PW) * PW;
+  for (int p0 = last; p0 >= 0; p0 -= PW) {
+    const int pw = std::min(PW, n - 1 - p0);
+    const int rows = n - p0;
+    zgemm_splitk(st, OP_C, OP_N, pw, k, rows, ONE, A_ + (long)p0 * lda_ + p0, lda_, U + p0, ldu, ZERO, X_, PW, &part_,
+                 &part_cap_);
+    zgemm(st, OP_N, OP_N, rows, k, pw, MONE, VT_ + (long)p0 * n + p0, n, X_, PW, ONE, U + p0, ldu);
+  }
+}
+
+}  // namespace tevo

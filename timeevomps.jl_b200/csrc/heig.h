@@ -1,0 +1,31 @@
+// Hermitian eigensolver (device): see heig.cu.
+#pragma once
+#include "common.cuh"
+#include "stedc.h"
+
+namespace tevo {
+
+class Heig {
+ public:
+  void init();
+  void destroy();
+  // Factor the n x n Hermitian matrix A (full storage, column-major; overwritten by the Householder reflectors).
+  // Afterwards evals() (ascending, device) is valid and vectors() can be called.  No host synchronisation.
+  void factor(cudaStream_t st, int n, cplx* A, long lda);
+  const double* evals() const { return evals_; }
+  // U(:, i) = eigenvector of column perm[i] (indices into the ascending order), i < k.  U is n x k, ld = ldu.
+  void vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ldu);
+
+ private:
+  void ensure(int n);
+  Stedc stedc_;
+  int num_sms_ = 148;
+  int cap_ = 0, n_ = 0;
+  cplx* A_ = nullptr;
+  long lda_ = 0;
+  cplx *P_ = nullptr, *Q_ = nullptr, *Y_ = nullptr, *VT_ = nullptr, *taus_ = nullptr, *Tblk_ = nullptr, *X_ = nullptr, *part_ = nullptr;
+  size_t xcap_ = 0, part_cap_ = 0;
+  double *d_ = nullptr, *e_ = nullptr, *evals_ = nullptr, *Z_ = nullptr, *acc_ = nullptr;
+};
+
+}  // namespace tevo

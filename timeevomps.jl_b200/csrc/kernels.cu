@@ -199,19 +199,7 @@ void colnorm2(cudaStream_t st, const cplx* X, long ld, int nr, int nc, double* o
 // On-device truncate! : sort sigma^2 descending (bitonic, one CTA), then the upstream rule
 // (ITensors truncate!) on thread 0; writes permutation, sorted values and TruncInfo.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncParams tp, double* __restrict__ sorted,
-                     int* __restrict__ perm, TruncInfo* __restrict__ info, int npow2) {
-  extern __shared__ unsigned char sm_raw[];
-  double* key = reinterpret_cast<double*>(sm_raw);
-  int* idx = reinterpret_cast<int*>(key + npow2);
-  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-    double v = (i < nc) ? lam[i] : -1.0;
-    if (!(v == v)) v = -0.5;  // NaN guard: sorts below every real weight, flagged later
-    key[i] = v;
-    idx[i] = i;
-  }
-  __syncthreads();
+__device__ inline void bitonic_desc(double* key, int* idx, int npow2) {
   for (int k = 2; k <= npow2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
@@ -233,6 +221,28 @@ sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncPar
       __syncthreads();
     }
   }
+}
+
+__global__ void __launch_bounds__(1024)
+sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncParams tp, double* __restrict__ sorted,
+                     int* __restrict__ perm, TruncInfo* __restrict__ info, int npow2) {
+  extern __shared__ unsigned char sm_raw[];
+  double* key = reinterpret_cast<double*>(sm_raw);
+  int* idx = reinterpret_cast<int*>(key + npow2);
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    double v = (i < nc) ? lam[i] : -INFINITY;  // padding sorts below every value
+    if (!(v == v)) {                           // NaN guard: flagged, sorted last
+      v = -INFINITY;
+      s_bad = 1;
+    }
+    key[i] = v;
+    idx[i] = i;
+  }
+  __syncthreads();
+  bitonic_desc(key, idx, npow2);
   for (int i = threadIdx.x; i < nc; i += blockDim.x) {
     sorted[i] = key[i];
     perm[i] = idx[i];
@@ -242,15 +252,19 @@ sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncPar
     const int origm = nfull;
     int n = origm;
     double truncerr = 0.0, sum_all = 0.0;
-    int bad = 0;
+    int bad = s_bad;
     for (int i = 0; i < origm; ++i) {
       double p = key[i];
       if (p < 0.0) {
-        if (p == -0.5) bad = 1;
+        if (p == -INFINITY) bad = 1;
         p = 0.0;
       }
-      key[i] = p;
       sum_all += p;
+      key[i] = p;
+    }
+    if (tp.inflate_rel > 0.0) {
+      const double infl = tp.inflate_rel * key[0];
+      for (int i = 0; i < origm; ++i) key[i] += infl;
     }
     if (key[0] <= 0.0 || origm == 1) {
       n = 1;
@@ -295,7 +309,119 @@ sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncPar
     info->sum_all = sum_all;
     info->sum_kept = sum_kept;
     info->bad = bad;
+    info->identity = 1;
   }
+}
+
+__global__ void __launch_bounds__(1024)
+refine_truncate_kernel(const double* __restrict__ lam2, int k1, int nfull, const double* __restrict__ sum_all_dev,
+                       const double* __restrict__ resid2_dev, TruncParams tp, double* __restrict__ sorted,
+                       int* __restrict__ perm, TruncInfo* __restrict__ info, int npow2) {
+  extern __shared__ unsigned char sm_raw[];
+  double* key = reinterpret_cast<double*>(sm_raw);
+  int* idx = reinterpret_cast<int*>(key + npow2);
+  __shared__ int s_bad, s_ident;
+  if (threadIdx.x == 0) {
+    s_bad = 0;
+    s_ident = 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+    double v = (i < k1) ? lam2[i] : -INFINITY;
+    if (!(v == v)) {
+      v = -INFINITY;
+      s_bad = 1;
+    }
+    key[i] = v;
+    idx[i] = i;
+  }
+  __syncthreads();
+  bitonic_desc(key, idx, npow2);
+  for (int i = threadIdx.x; i < k1; i += blockDim.x) {
+    sorted[i] = key[i];
+    perm[i] = idx[i];
+    if (idx[i] != i) s_ident = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double sum_all = *sum_all_dev;
+    double truncerr = (k1 < nfull) ? fmax(*resid2_dev, 0.0) : 0.0;  // absolute weight discarded in stage 1
+    int n = k1;
+    if (tp.do_truncate && !(key[0] <= 0.0) && k1 > 1) {
+      const int mindim = tp.mindim > 1 ? tp.mindim : 1;
+      const double cutoff = tp.cutoff > 0.0 ? tp.cutoff : 0.0;
+      if (tp.use_absolute_cutoff) {
+        while (key[n - 1] <= cutoff && n > mindim) {
+          truncerr += key[n - 1];
+          --n;
+        }
+      } else {
+        double scale = 1.0;
+        if (tp.do_rel_cutoff) scale = (sum_all == 0.0) ? 1.0 : sum_all;
+        while ((truncerr + key[n - 1] <= cutoff * scale) && n > mindim) {
+          truncerr += key[n - 1];
+          --n;
+        }
+      }
+    } else if (key[0] <= 0.0) {
+      n = 1;
+    }
+    if (!tp.use_absolute_cutoff && tp.do_truncate) {
+      double scale = 1.0;
+      if (tp.do_rel_cutoff) scale = (sum_all == 0.0) ? 1.0 : sum_all;
+      truncerr /= scale;
+    }
+    if (n == nfull) truncerr = 0.0;
+    double sum_kept = 0.0, ent = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double p = key[i];
+      sum_kept += p;
+      if (p > 1e-13) ent -= p * log(p);
+    }
+    info->nkeep = n;
+    info->nfull = nfull;
+    info->truncerr = truncerr;
+    info->entropy = ent;
+    info->sum_all = sum_all;
+    info->sum_kept = sum_kept;
+    info->bad = s_bad;
+    info->identity = s_ident;
+  }
+}
+
+void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, const double* sum_all_dev,
+                     const double* resid2_dev, const TruncParams& tp, double* sorted, int* perm, TruncInfo* info) {
+  int npow2 = 1;
+  while (npow2 < k1) npow2 <<= 1;
+  if (npow2 > 8192) throw TevoError(1, "refine_truncate: more than 8192 singular values not supported");
+  size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
+  static bool configured = false;
+  if (!configured) {
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(refine_truncate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+    configured = true;
+  }
+  int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;
+  refine_truncate_kernel<<<1, threads, smem, st>>>(lam2, k1, nfull, sum_all_dev, resid2_dev, tp, sorted, perm, info, npow2);
+  TEVO_LAUNCHED();
+}
+
+// dst(i, :) = scale * src(perm[i], :)   (k x n, row gather)
+__global__ void gather_rows_kernel(int k, int n, const cplx* __restrict__ src, long lds, const int* __restrict__ perm,
+                                   cplx* __restrict__ dst, long ldd, const double* __restrict__ norm2) {
+  double sc = 1.0;
+  if (norm2 && (*norm2 > 0.0)) sc = rsqrt(*norm2);
+  const long total = (long)k * n;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % k);
+    const long j = e / k;
+    dst[j * ldd + i] = cscale(sc, src[j * lds + perm[i]]);
+  }
+}
+void gather_rows(cudaStream_t st, int k, int n, const cplx* src, long lds, const int* perm, cplx* dst, long ldd,
+                 const double* norm2) {
+  if (k <= 0 || n <= 0) return;
+  gather_rows_kernel<<<grid_for((long)k * n), 256, 0, st>>>(k, n, src, lds, perm, dst, ldd, norm2);
+  TEVO_LAUNCHED();
 }
 
 void sort_truncate(cudaStream_t st, const double* lam, int nc, int nfull, const TruncParams& tp, double* sorted,

@@ -7,11 +7,13 @@ struct TruncParams {
   int has_maxdim, maxdim, mindim;
   double cutoff;
   int use_absolute_cutoff, do_rel_cutoff;
+  double inflate_rel;  // stage-1 (Gram spectrum) safety margin: every weight is raised by inflate_rel * largest weight
 };
 struct TruncInfo {
   int nkeep, nfull;
   double truncerr, entropy, sum_all, sum_kept;
   int bad;
+  int identity;  // stage 2: kept rows are already in descending order
 };
 
 void gate_apply(cudaStream_t st, cplx* theta, int chil, int d, int chir, const cplx* G_dev);
@@ -22,6 +24,12 @@ void jacobi_round(cudaStream_t st, cplx* X, long ldx, int nrx, cplx* V, long ldv
 void colnorm2(cudaStream_t st, const cplx* X, long ld, int nr, int nc, double* out);
 void sort_truncate(cudaStream_t st, const double* lam, int nc, int nfull, const TruncParams& tp, double* sorted,
                    int* perm, TruncInfo* info);
+// stage 2 of the split: sort the Rayleigh-refined weights of the k1 candidate rows, continue upstream's truncate! loop
+// from n = k1 with the accurately known discarded weight *resid2 (absolute), fill the final Spectrum summary
+void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, const double* sum_all_dev,
+                     const double* resid2_dev, const TruncParams& tp, double* sorted, int* perm, TruncInfo* info);
+void gather_rows(cudaStream_t st, int k, int n, const cplx* src, long lds, const int* perm, cplx* dst, long ldd,
+                 const double* norm2);
 void gather_cols(cudaStream_t st, int nr, int k, const cplx* src, long lds, const int* perm, cplx* dst, long ldd,
                  const double* norm2);
 void gather_cols_conjT(cudaStream_t st, int nr, int k, const cplx* src, long lds, const int* perm, cplx* dst,

@@ -2,8 +2,10 @@
 // ITensors.replacebond!/factorize/svd/truncate! as called from src/bondgate.jl:51 and src/tdvp.jl:64.
 #pragma once
 #include <functional>
+#include <vector>
 
 #include "common.cuh"
+#include "heig.h"
 #include "kernels.h"
 
 namespace tevo {
@@ -28,9 +30,30 @@ class Split {
   // eigs (host, optional): kept sigma^2, descending.  alloc: allocator for the two outputs.
   SplitResult run(cudaStream_t st, const cplx* theta, int m, int n, bool left, const TruncParams& tp, bool normalize,
                   double* eigs, int eigs_cap, const std::function<DevBuf(size_t)>& alloc);
+  // orthogonal factorisation used by the centre moves of orthogonalize! (no truncation, no normalisation):
+  //   left : A (m x n) = Q (m x k) * C (k x n),  Q^H Q = 1      right: A = C (m x k) * Q (k x n),  Q Q^H = 1
+  SplitResult ortho_factor(cudaStream_t st, const cplx* A, int m, int n, bool left,
+                           const std::function<DevBuf(size_t)>& alloc);
+  // buffers replaced by a stage-2 re-gather; the owner returns them to its pool with take_released()
+  std::vector<DevBuf> take_released() {
+    std::vector<DevBuf> r;
+    r.swap(pending_release_);
+    return r;
+  }
+  Heig& heig() { return heig_; }
+  int* perm_dev() { return d_perm_; }
+  double* sorted_dev() { return d_sorted_; }
+  void reserve_vec(size_t n) { ensure_vec(n); }
+  TruncInfo* info_dev() { return d_info_; }
   int last_sweeps = 0;
+  bool use_jacobi = false;  // TEVO_SPLIT_JACOBI=1: first-generation Hestenes path (slow, kept as a cross-check)
 
  private:
+  SplitResult run_jacobi(cudaStream_t st, const cplx* theta, int m, int n, bool left, const TruncParams& tp,
+                         bool normalize, double* eigs, int eigs_cap, const std::function<DevBuf(size_t)>& alloc);
+  Heig heig_;
+  std::vector<DevBuf> pending_release_;
+  double* d_scal_ = nullptr;  // [0..1] |theta|^2, [2..3] |residual|^2
   cplx* ws(int slot, size_t nelem);
   DevBuf ws_[4];
   double* d_lam_ = nullptr;

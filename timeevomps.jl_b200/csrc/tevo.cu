@@ -10,6 +10,7 @@
 #include "../../include/tevo.h"
 #include "common.cuh"
 #include "kernels.h"
+#include "prof.h"
 #include "split.h"
 #include "zgemm.h"
 
@@ -186,18 +187,21 @@ static const cplx ONE = {1.0, 0.0}, ZERO = {0.0, 0.0};
 static void set_site(tevo_mps* psi, int j, DevBuf nb) {
   psi->ctx->release(psi->site[j]);
   psi->site[j] = nb;
+  for (auto& b : psi->ctx->split.take_released()) psi->ctx->release(b);
 }
 
 // centre j -> j+1 (QR-equivalent hop of orthogonalize!; here an untruncated split U * (S V^+))
 static void hop_right(tevo_mps* psi, int j) {
   tevo_ctx* c = psi->ctx;
   const int d = psi->d, m = psi->chi[j] * d, n = psi->chi[j + 1];
-  TruncParams tp = to_params(nullptr);
-  SplitResult r = c->split.run(c->stream, psi->site[j].p, m, n, /*left=*/true, tp, /*normalize=*/false, nullptr, 0,
-                               [&](size_t ne) { return c->alloc(ne); });
+  SplitResult r = c->split.ortho_factor(c->stream, psi->site[j].p, m, n, /*left=*/true,
+                                        [&](size_t ne) { return c->alloc(ne); });
   const int k = r.k, n2 = d * psi->chi[j + 2];
   DevBuf nb = c->alloc((size_t)k * n2);
-  zgemm(c->stream, OP_N, OP_N, k, n2, n, ONE, r.R.p, k, psi->site[j + 1].p, n, ZERO, nb.p, k);
+  {
+    ProfScope ps(c->stream, P_HOP_GEMM);
+    zgemm(c->stream, OP_N, OP_N, k, n2, n, ONE, r.R.p, k, psi->site[j + 1].p, n, ZERO, nb.p, k);
+  }
   c->release(r.R);
   set_site(psi, j, r.L);
   set_site(psi, j + 1, nb);
@@ -208,12 +212,14 @@ static void hop_right(tevo_mps* psi, int j) {
 static void hop_left(tevo_mps* psi, int j) {
   tevo_ctx* c = psi->ctx;
   const int d = psi->d, m = psi->chi[j], n = d * psi->chi[j + 1];
-  TruncParams tp = to_params(nullptr);
-  SplitResult r = c->split.run(c->stream, psi->site[j].p, m, n, /*left=*/false, tp, false, nullptr, 0,
-                               [&](size_t ne) { return c->alloc(ne); });
+  SplitResult r = c->split.ortho_factor(c->stream, psi->site[j].p, m, n, /*left=*/false,
+                                        [&](size_t ne) { return c->alloc(ne); });
   const int k = r.k, m2 = psi->chi[j - 1] * d;
   DevBuf nb = c->alloc((size_t)m2 * k);
-  zgemm(c->stream, OP_N, OP_N, m2, k, m, ONE, psi->site[j - 1].p, m2, r.L.p, m, ZERO, nb.p, m2);
+  {
+    ProfScope ps(c->stream, P_HOP_GEMM);
+    zgemm(c->stream, OP_N, OP_N, m2, k, m, ONE, psi->site[j - 1].p, m2, r.L.p, m, ZERO, nb.p, m2);
+  }
   c->release(r.L);
   set_site(psi, j, r.R);
   set_site(psi, j - 1, nb);
@@ -252,6 +258,7 @@ static cplx* form_theta(tevo_mps* psi, int b, int slot = WS_THETA) {
   tevo_ctx* c = psi->ctx;
   const int d = psi->d, m = psi->chi[b] * d, k = psi->chi[b + 1], n = d * psi->chi[b + 2];
   cplx* th = c->get_ws(slot, (size_t)m * n);
+  ProfScope ps(c->stream, P_THETA);
   zgemm(c->stream, OP_N, OP_N, m, n, k, ONE, psi->site[b].p, m, psi->site[b + 1].p, k, ZERO, th, m);
   return th;
 }
@@ -284,8 +291,11 @@ static TruncInfo apply_gate_dev(tevo_mps* psi, int b, const cplx* G_dev, const T
     orthogonalize(psi, b);  // src/bondgate.jl:48
   else
     center_into_pair(psi, b);
-  cplx* th = form_theta(psi, b);                                           // src/bondgate.jl:50
-  gate_apply(c->stream, th, psi->chi[b], psi->d, psi->chi[b + 2], G_dev);  // G * theta, noprime
+  cplx* th = form_theta(psi, b);  // src/bondgate.jl:50
+  {
+    ProfScope ps(c->stream, P_GATE);
+    gate_apply(c->stream, th, psi->chi[b], psi->d, psi->chi[b + 2], G_dev);  // G * theta, noprime
+  }
   return replace_bond(psi, b, th, left, tp, normalize, eigs, eigs_cap);    // src/bondgate.jl:51
 }
 
@@ -903,6 +913,7 @@ struct Heff {
   int P, Q;
   long n;  // vector length
   void apply(const cplx* v, cplx* out) const {
+    ProfScope ps(c->stream, P_HEFF);
     const int dd = (nsite == 2) ? d * d : d;
     cplx* T1 = c->get_ws(WS_T1, (size_t)cl * wl * dd * cr);
     zgemm(c->stream, OP_N, OP_N, cl * wl, dd * cr, cl, ONE, L, cl * wl, v, cl, ZERO, T1, cl * wl);
@@ -1250,4 +1261,37 @@ extern "C" int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* 
   ctx->release(r.R);
   ctx->release(dT);
   TEVO_CATCH
+}
+
+extern "C" int tevo_test_heig(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U) {
+  TEVO_TRY(ctx)
+  require(ctx && A && evals_desc && U && n >= 1, "tevo_test_heig: bad argument");
+  DevBuf dA = ctx->alloc((size_t)n * n), dU = ctx->alloc((size_t)n * n);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(dA.p, A, (size_t)n * n * sizeof(cplx), cudaMemcpyHostToDevice, ctx->stream));
+  Split& sp = ctx->split;
+  sp.reserve_vec((size_t)n);
+  sp.heig().factor(ctx->stream, n, dA.p, n);
+  TruncParams tp = to_params(nullptr);
+  sort_truncate(ctx->stream, sp.heig().evals(), n, n, tp, sp.sorted_dev(), sp.perm_dev(), sp.info_dev());
+  sp.heig().vectors(ctx->stream, sp.perm_dev(), n, dU.p, n);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(evals_desc, sp.sorted_dev(), sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(U, dU.p, (size_t)n * n * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+  TEVO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->release(dA);
+  ctx->release(dU);
+  TEVO_CATCH
+}
+
+extern "C" int tevo_profile_enable(int on) {
+  tevo::g_prof.on = (on != 0);
+  return TEVO_OK;
+}
+
+/* JSON {"phase": {"ms": total device time, "count": n}, ...} of the phases timed since the last reset */
+extern "C" int tevo_profile_read(char* buf, size_t cap, int reset) {
+  if (!buf || cap == 0) return TEVO_EINVAL;
+  std::string s = tevo::g_prof.json(reset != 0);
+  if (s.size() + 1 > cap) return TEVO_EINVAL;
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return TEVO_OK;
 }

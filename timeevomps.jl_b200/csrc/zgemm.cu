@@ -66,8 +66,15 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1)
-zgemm_dmma_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
-                  const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc) {
+zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
+                  const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
+                  long part_stride) {
+  // split-K: CTA z handles k in [z*Kc, min(Kfull, (z+1)*Kc)) and writes its partial product to C + z*part_stride
+  const int kb = blockIdx.z * Kc;
+  const int K = min(Kfull - kb, Kc);
+  A += A_KMAJOR ? (long)kb : (long)kb * lda;
+  B += B_KMAJOR ? (long)kb : (long)kb * ldb;
+  C += (long)blockIdx.z * part_stride;
   typedef Tile<BM, A_KMAJOR> TA;
   typedef Tile<BN, B_KMAJOR> TB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -171,7 +178,7 @@ zgemm_dmma_kernel(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, l
 
 template <bool AK, bool BK_>
 void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
-            long ldb, int conjB, cplx beta, cplx* C, long ldc) {
+            long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0) {
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
@@ -181,8 +188,9 @@ void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, lon
                                          (int)smem));
     configured = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc);
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc,
+                                                          splits > 1 ? Kc : K, part_stride);
   TEVO_LAUNCHED();
 }
 
@@ -194,6 +202,29 @@ __global__ void zscale_matrix_kernel(int M, int N, cplx beta, cplx* C, long ldc)
     cplx* p = C + j * ldc + i;
     *p = (beta.x == 0.0 && beta.y == 0.0) ? mk(0, 0) : cmul(beta, *p);
   }
+}
+
+// C = alpha * sum_z part_z + beta * C
+__global__ void splitk_reduce_kernel(int M, int N, int splits, const cplx* __restrict__ part, long part_stride,
+                                     cplx alpha, cplx beta, cplx* __restrict__ C, long ldc) {
+  const long total = (long)M * N;
+  const bool has_beta = (beta.x != 0.0 || beta.y != 0.0);
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    cplx s = mk(0, 0);
+    for (int z = 0; z < splits; ++z) s = cadd(s, part[(long)z * part_stride + e]);
+    const int i = (int)(e % M);
+    const long j = e / M;
+    cplx v = cmul(alpha, s);
+    cplx* dst = C + j * ldc + i;
+    if (has_beta) v = cadd(v, cmul(beta, *dst));
+    *dst = v;
+  }
+}
+
+template <bool AK, bool BK_>
+void launch_split(cudaStream_t st, int M, int N, int K, const cplx* A, long lda, int conjA, const cplx* B, long ldb,
+                  int conjB, cplx* part, int splits, int Kc) {
+  launch<AK, BK_>(st, M, N, K, mk(1, 0), A, lda, conjA, B, ldb, conjB, mk(0, 0), part, M, splits, Kc, (long)M * N);
 }
 
 }  // namespace
@@ -224,6 +255,49 @@ void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const
     launch<false, true>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
   else
     launch<false, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
+}
+
+
+// Split-K variant for skinny outputs (few CTA tiles, long K): deterministic two-pass (partials + reduce).
+void zgemm_splitk(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
+                  long ldb, cplx beta, cplx* C, long ldc, cplx** part, size_t* part_cap) {
+  if (M <= 0 || N <= 0) return;
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int splits = 148 / (tiles > 0 ? tiles : 1);
+  const int maxs = (K + 4 * BK - 1) / (4 * BK);
+  if (splits > maxs) splits = maxs;
+  if (splits > 32) splits = 32;
+  if (splits <= 1) {
+    zgemm(st, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return;
+  }
+  int Kc = (K + splits - 1) / splits;
+  Kc = ((Kc + BK - 1) / BK) * BK;
+  splits = (K + Kc - 1) / Kc;
+  const size_t need = (size_t)splits * M * N;
+  if (*part_cap < need) {
+    if (*part) TEVO_CUDA_CHECK(cudaFree(*part));
+    *part = nullptr;
+    *part_cap = 0;
+    TEVO_CUDA_CHECK(cudaMalloc(part, need * sizeof(cplx)));
+    *part_cap = need;
+  }
+  ++g_zgemm_launches;
+  const bool ak = (ta != OP_N), bk = (tb == OP_N);
+  const int ca = (ta == OP_C), cb = (tb == OP_C);
+  if (ak && bk)
+    launch_split<true, true>(st, M, N, K, A, lda, ca, B, ldb, cb, *part, splits, Kc);
+  else if (ak && !bk)
+    launch_split<true, false>(st, M, N, K, A, lda, ca, B, ldb, cb, *part, splits, Kc);
+  else if (!ak && bk)
+    launch_split<false, true>(st, M, N, K, A, lda, ca, B, ldb, cb, *part, splits, Kc);
+  else
+    launch_split<false, false>(st, M, N, K, A, lda, ca, B, ldb, cb, *part, splits, Kc);
+  const long total = (long)M * N;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  splitk_reduce_kernel<<<blocks, 256, 0, st>>>(M, N, splits, *part, (long)M * N, alpha, beta, C, ldc);
+  TEVO_LAUNCHED();
 }
 
 }  // namespace tevo

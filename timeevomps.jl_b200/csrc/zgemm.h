@@ -4,5 +4,7 @@ namespace tevo {
 // C = alpha*op(A)*op(B) + beta*C, column-major, complex FP64 on the DMMA pipe.
 void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
            long ldb, cplx beta, cplx* C, long ldc);
+void zgemm_splitk(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
+                  long ldb, cplx beta, cplx* C, long ldc, cplx** part, size_t* part_cap);
 extern long g_zgemm_launches;
 }  // namespace tevo
