@@ -173,8 +173,8 @@ class MPS:
             # bring to right-canonical form, centre at 0
             for j in range(N - 1, 0, -1):
                 psi._hop_left(j)
+                psi.A[j - 1] /= np.linalg.norm(psi.A[j - 1])  # keeps long chains from overflowing
             psi.llim, psi.rlim = -1, 1
-            psi.A[0] /= np.linalg.norm(psi.A[0])
         return psi
 
     # ---- orthogonalize! [UPSTREAM]: QR hops moving the centre ----

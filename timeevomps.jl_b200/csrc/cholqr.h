@@ -1,0 +1,24 @@
+// CholeskyQR2 (see cholqr.cu)
+#pragma once
+#include "common.cuh"
+
+namespace tevo {
+
+class CholQR {
+ public:
+  void init();
+  void destroy();
+  // A (m x n, ld m, m >= n) = Q (m x n, ld m) * C (n x n, ld n).  Returns false (outputs undefined) when A is too
+  // ill-conditioned for the method; synchronises the stream twice (pivot checks).
+  bool factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx* C);
+
+ private:
+  void ensure(int m, int n);
+  void pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q);
+  cplx *G_ = nullptr, *L1_ = nullptr, *L2_ = nullptr, *Linv_ = nullptr, *T_ = nullptr, *Q1_ = nullptr;
+  double *d_stats_ = nullptr, *h_stats_ = nullptr;
+  int ncap_ = 0;
+  size_t mcap_ = 0;
+};
+
+}  // namespace tevo

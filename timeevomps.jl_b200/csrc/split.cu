@@ -17,6 +17,11 @@ namespace tevo {
 
 void Split::init(cudaStream_t) {
   heig_.init();
+  cholqr_.init();
+  {
+    const char* e2 = getenv("TEVO_NO_CHOLQR");
+    use_cholqr_ = !(e2 && e2[0] == '1');
+  }
   TEVO_CUDA_CHECK(cudaMalloc(&d_scal_, sizeof(double) * 8));
   const char* env = getenv("TEVO_SPLIT_JACOBI");
   use_jacobi = (env && env[0] == '1');
@@ -28,6 +33,7 @@ void Split::init(cudaStream_t) {
 
 void Split::destroy() {
   heig_.destroy();
+  cholqr_.destroy();
   if (d_scal_) cudaFree(d_scal_);
   for (auto& b : ws_)
     if (b.p) cudaFree(b.p);
@@ -323,6 +329,36 @@ SplitResult Split::ortho_factor(cudaStream_t st, const cplx* A, int m, int n, bo
   if (use_jacobi || (left && m < n) || (!left && m > n)) return run(st, A, m, n, left, tp, false, nullptr, 0, alloc);
   const cplx ONE = mk(1, 0), ZERO = mk(0, 0);
   const int k = left ? n : m;
+  if (use_cholqr_ && k >= 2) {
+    // fast path: CholeskyQR2 (well-conditioned centre tensors); the right case works on A^H
+    SplitResult res;
+    res.k = k;
+    memset(&res.info, 0, sizeof(res.info));
+    res.info.nkeep = res.info.nfull = k;
+    res.L = alloc((size_t)m * k);
+    res.R = alloc((size_t)k * n);
+    bool ok;
+    if (left) {
+      ok = cholqr_.factor(st, A, m, n, res.L.p, res.R.p);
+    } else {
+      cplx* At = ws(0, (size_t)n * m);
+      cplx* Qt = ws(1, (size_t)n * m);
+      cplx* Ct = ws(2, (size_t)m * m);
+      conj_transpose(st, m, n, A, m, At, n, true);
+      ok = cholqr_.factor(st, At, n, m, Qt, Ct);
+      if (ok) {
+        conj_transpose(st, n, m, Qt, n, res.R.p, m, true);  // Q (m x n) = Qt^H
+        conj_transpose(st, m, m, Ct, m, res.L.p, m, true);  // C (m x m) = Ct^H
+      }
+    }
+    if (ok) {
+      ++cholqr_used;
+      return res;
+    }
+    ++cholqr_fallback;
+    pending_release_.push_back(res.L);
+    pending_release_.push_back(res.R);
+  }
   cplx* G = ws(0, (size_t)k * k);
   ensure_vec((size_t)k);
   {

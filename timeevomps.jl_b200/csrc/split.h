@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cholqr.h"
 #include "heig.h"
 #include "kernels.h"
 
@@ -45,6 +46,7 @@ class Split {
   double* sorted_dev() { return d_sorted_; }
   void reserve_vec(size_t n) { ensure_vec(n); }
   TruncInfo* info_dev() { return d_info_; }
+  long cholqr_used = 0, cholqr_fallback = 0;
   int last_sweeps = 0;
   bool use_jacobi = false;  // TEVO_SPLIT_JACOBI=1: first-generation Hestenes path (slow, kept as a cross-check)
 
@@ -52,6 +54,8 @@ class Split {
   SplitResult run_jacobi(cudaStream_t st, const cplx* theta, int m, int n, bool left, const TruncParams& tp,
                          bool normalize, double* eigs, int eigs_cap, const std::function<DevBuf(size_t)>& alloc);
   Heig heig_;
+  CholQR cholqr_;
+  bool use_cholqr_ = true;  // TEVO_NO_CHOLQR=1 disables the fast centre-move path
   std::vector<DevBuf> pending_release_;
   double* d_scal_ = nullptr;  // [0..1] |theta|^2, [2..3] |residual|^2
   cplx* ws(int slot, size_t nelem);

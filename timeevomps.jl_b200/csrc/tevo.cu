@@ -531,11 +531,17 @@ extern "C" int tevo_mps_random(tevo_mps* psi, int chi, unsigned long long seed) 
   psi->chi = dims;
   psi->llim = -1;
   psi->rlim = N;
-  orthogonalize(psi, 0);
-  // normalise the centre
-  size_t ne0 = (size_t)psi->chi[0] * d * psi->chi[1];
-  zdotc(c->stream, (long)ne0, psi->site[0].p, psi->site[0].p, c->d_scal);
-  zscal_rsqrt(c->stream, (long)ne0, c->d_scal, psi->site[0].p);
+  // right-canonicalise towards site 0; the receiving tensor is renormalised after every hop (the norm of a chain
+  // of N(0,1) tensors grows like (d*chi)^(N/2) and would overflow for long chains)
+  for (int j = N - 1; j >= 1; --j) {
+    hop_left(psi, j);
+    psi->rlim = j;
+    size_t ne = (size_t)psi->chi[j - 1] * d * psi->chi[j];
+    zdotc(c->stream, (long)ne, psi->site[j - 1].p, psi->site[j - 1].p, c->d_scal);
+    zscal_rsqrt(c->stream, (long)ne, c->d_scal, psi->site[j - 1].p);
+  }
+  psi->llim = -1;
+  psi->rlim = 1;
   TEVO_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   TEVO_CATCH
 }
