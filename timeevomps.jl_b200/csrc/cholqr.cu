@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 #include "kernels.h"
 #include "prof.h"
@@ -17,97 +18,75 @@ namespace {
 
 constexpr int NB = 64;
 
-// Cholesky of one NB x NB (or smaller, nb) diagonal block of G at (j,j); writes L_jj into Lm (upper part zeroed),
-// its inverse into Linv (NB x NB, ld NB), and the extreme pivots into stats[2*blk], stats[2*blk+1] (min < 0: failed)
-__global__ void __launch_bounds__(256) potrf_block_kernel(int nb, const cplx* __restrict__ G, long ldg, cplx* __restrict__ Lm,
-                                                          long ldl, cplx* __restrict__ Linv, double* __restrict__ stats) {
+// Cholesky of one nb x nb (nb <= 64) diagonal block of G at (j,j), left-looking, one thread per row: writes L_jj
+// into Lm (lower part) and its inverse into Xm (lower part) at the same position (both column-major, ld),
+// and the extreme pivots into stats[0..1] (stats[0] < 0: breakdown).
+__global__ void __launch_bounds__(64) potrf_block_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
+                                                         cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  cplx(*a)[NB + 1] = reinterpret_cast<cplx(*)[NB + 1]>(smraw);        // a[i][j]
-  cplx(*x)[NB + 1] = a + NB;                                           // inverse
-  __shared__ double s_min, s_max;
+  cplx(*a)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw);  // a[p][i] = L(i,p)   (column p contiguous over rows i)
+  cplx(*x)[NB] = a + NB;                                // x[p][c] = inv(L)(p,c)
+  __shared__ double s_piv;
   __shared__ int s_fail;
-  const int tid = threadIdx.x;
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e % NB, j = e / NB;
-    a[i][j] = (i < nb && j < nb) ? G[(long)j * ldg + i] : mk(i == j ? 1.0 : 0.0, 0.0);
-    x[i][j] = mk(0, 0);
-  }
-  if (tid == 0) {
-    s_min = 1e300;
-    s_max = 0.0;
-    s_fail = 0;
-  }
+  const int i = threadIdx.x;
+  for (int p = 0; p < nb; ++p) a[p][i] = (i < nb) ? G[(long)p * ld + i] : mk(0, 0);
+  if (i == 0) s_fail = 0;
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    const double dkk = a[k][k].x;
-    __syncthreads();
-    if (!(dkk > 0.0) || !isfinite(dkk)) {
-      if (tid == 0) s_fail = 1;
-      break;
+  double pmin = 1e300, pmax = 0.0;
+  for (int j = 0; j < nb; ++j) {
+    cplx sres = mk(0, 0);
+    if (i >= j && i < nb) {
+      sres = a[j][i];
+      for (int p = 0; p < j; ++p) sres = csub(sres, cmul(a[p][i], cconj(a[p][j])));
     }
-    const double l = sqrt(dkk);
-    if (tid == 0) {
-      a[k][k] = mk(l, 0.0);
-      s_min = fmin(s_min, l);
-      s_max = fmax(s_max, l);
-    }
-    const double inv = 1.0 / l;
-    for (int i = k + 1 + tid; i < nb; i += blockDim.x) a[i][k] = cscale(inv, a[i][k]);
-    __syncthreads();
-    // trailing update of the lower triangle: a[i][j] -= a[i][k] conj(a[j][k]),  k < j <= i
-    const int rem = nb - k - 1;
-    for (int e = tid; e < rem * rem; e += blockDim.x) {
-      const int i = k + 1 + e % rem, j = k + 1 + e / rem;
-      if (j <= i) {
-        const cplx p = cmul(a[i][k], cconj(a[j][k]));
-        a[i][j] = csub(a[i][j], p);
+    if (i == j) {
+      const double dkk = sres.x;
+      if (!(dkk > 0.0) || !isfinite(dkk)) {
+        s_fail = 1;
+        s_piv = 1.0;
+      } else {
+        s_piv = sqrt(dkk);
       }
     }
     __syncthreads();
+    if (s_fail) break;
+    const double l = s_piv;
+    pmin = fmin(pmin, l);
+    pmax = fmax(pmax, l);
+    if (i >= j && i < nb) a[j][i] = (i == j) ? mk(l, 0.0) : cscale(1.0 / l, sres);
+    __syncthreads();
   }
-  __syncthreads();
   if (s_fail) {
-    if (tid == 0) {
+    if (i == 0) {
       stats[0] = -1.0;
       stats[1] = 0.0;
     }
     return;
   }
-  // inverse of the lower-triangular factor, one thread per column (forward substitution)
-  if (tid < nb) {
-    const int j = tid;
-    for (int i = j; i < nb; ++i) {
-      cplx s = mk(i == j ? 1.0 : 0.0, 0.0);
-      for (int p = j; p < i; ++p) s = csub(s, cmul(a[i][p], x[p][j]));
-      x[i][j] = cscale(1.0 / a[i][i].x, s);
+  // inverse by forward substitution, thread c owns column c
+  const int c = i;
+  if (c < nb) {
+    for (int r = 0; r < nb; ++r) {
+      if (r < c) {
+        x[r][c] = mk(0, 0);
+        continue;
+      }
+      cplx sres = mk(r == c ? 1.0 : 0.0, 0.0);
+      for (int p = c; p < r; ++p) sres = csub(sres, cmul(a[p][r], x[p][c]));
+      x[r][c] = cscale(1.0 / a[r][r].x, sres);
     }
   }
   __syncthreads();
-  for (int e = tid; e < nb * nb; e += blockDim.x) {
-    const int i = e % nb, j = e / nb;
-    Lm[(long)j * ldl + i] = (j <= i) ? a[i][j] : mk(0, 0);
+  for (int p = 0; p < nb; ++p) {
+    if (i < nb) {
+      Lm[(long)p * ld + i] = (i >= p) ? a[p][i] : mk(0, 0);
+      Xm[(long)p * ld + i] = (i >= p) ? x[i][p] : mk(0, 0);
+    }
   }
-  for (int e = tid; e < NB * NB; e += blockDim.x) {
-    const int i = e % NB, j = e / NB;
-    Linv[(long)j * NB + i] = (i < nb && j < nb) ? x[i][j] : mk(0, 0);
+  if (i == 0) {
+    stats[0] = pmin;
+    stats[1] = pmax;
   }
-  if (tid == 0) {
-    stats[0] = s_min;
-    stats[1] = s_max;
-  }
-}
-
-__global__ void zero_upper_block_kernel(int rows, int cols, cplx* __restrict__ M, long ld) {
-  const long total = (long)rows * cols;
-  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
-    M[(e / rows) * ld + (e % rows)] = mk(0, 0);
-}
-
-inline int gridfor(long total) {
-  long b = (total + 255) / 256;
-  if (b < 1) b = 1;
-  if (b > 148 * 8) b = 148 * 8;
-  return (int)b;
 }
 
 }  // namespace
@@ -116,7 +95,7 @@ void CholQR::init() {
   TEVO_CUDA_CHECK(cudaMalloc(&d_stats_, sizeof(double) * 2 * 128));
   TEVO_CUDA_CHECK(cudaMallocHost(&h_stats_, sizeof(double) * 2 * 128));
   TEVO_CUDA_CHECK(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(2 * sizeof(cplx) * NB * (NB + 1))));
+                                       (int)(2 * sizeof(cplx) * NB * NB)));
 }
 
 void CholQR::destroy() {
@@ -140,51 +119,60 @@ void CholQR::ensure(int m, int n) {
     TEVO_CUDA_CHECK(cudaMalloc(&G_, sizeof(cplx) * nn));
     TEVO_CUDA_CHECK(cudaMalloc(&L1_, sizeof(cplx) * nn));
     TEVO_CUDA_CHECK(cudaMalloc(&L2_, sizeof(cplx) * nn));
-    TEVO_CUDA_CHECK(cudaMalloc(&Linv_, sizeof(cplx) * (size_t)NB * NB * ((n + NB - 1) / NB)));
+    TEVO_CUDA_CHECK(cudaMalloc(&Linv_, sizeof(cplx) * nn));
     ncap_ = n;
     mcap_ = 0;
   }
   if ((size_t)m * n > mcap_) {
     if (T_) cudaFree(T_);
     if (Q1_) cudaFree(Q1_);
-    TEVO_CUDA_CHECK(cudaMalloc(&T_, sizeof(cplx) * (size_t)m * NB));
+    TEVO_CUDA_CHECK(cudaMalloc(&T_, sizeof(cplx) * std::max((size_t)m * NB, (size_t)n * n)));
     TEVO_CUDA_CHECK(cudaMalloc(&Q1_, sizeof(cplx) * (size_t)m * n));
     mcap_ = (size_t)m * n;
   }
 }
 
-// one pass: Q = A L^-H with A^H A = L L^H; returns the pivot extremes through stats (device)
+// one pass: Q = A L^-H with A^H A = L L^H; pivot extremes per diagonal block go to d_stats_
 void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q) {
   const cplx ONE = mk(1, 0), ZERO = mk(0, 0), MONE = mk(-1, 0);
   const int nblk = (n + NB - 1) / NB;
+  cplx* X = Linv_;  // n x n: inverse of L, assembled below
+  TEVO_CUDA_CHECK(cudaMemsetAsync(L, 0, sizeof(cplx) * (size_t)n * n, st));
+  TEVO_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(cplx) * (size_t)n * n, st));
   zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G_, n);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
-    potrf_block_kernel<<<1, 256, 2 * sizeof(cplx) * NB * (NB + 1), st>>>(nb, G_ + (long)j * n + j, n, L + (long)j * n + j, n,
-                                                                       Linv_ + (size_t)jb * NB * NB, d_stats_ + 2 * jb);
+    potrf_block_kernel<<<1, 64, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
+                                         d_stats_ + 2 * jb);
     TEVO_LAUNCHED();
-    if (j > 0) {  // zero the block row above the diagonal block (strictly upper part of L)
-      zero_upper_block_kernel<<<gridfor((long)j * nb), 256, 0, st>>>(j, nb, L + (long)j * n, n);
-      TEVO_LAUNCHED();
-    }
     if (rest > 0) {
-      // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H
-      zgemm(st, OP_N, OP_C, rest, nb, nb, ONE, G_ + (long)j * n + j + nb, n, Linv_ + (size_t)jb * NB * NB, NB, ZERO,
+      // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H ; trailing: G(j+nb:, j+nb:) -= panel * panel^H
+      zgemm(st, OP_N, OP_C, rest, nb, nb, ONE, G_ + (long)j * n + j + nb, n, X + (long)j * n + j, n, ZERO,
             L + (long)j * n + j + nb, n);
-      // trailing: G(j+nb:, j+nb:) -= panel * panel^H
       zgemm(st, OP_N, OP_C, rest, rest, nb, MONE, L + (long)j * n + j + nb, n, L + (long)j * n + j + nb, n, ONE,
             G_ + (long)(j + nb) * n + j + nb, n);
     }
   }
-  // Q = A L^-H by block forward substitution over the block columns
-  for (int jb = 0; jb < nblk; ++jb) {
-    const int j = jb * NB, nb = std::min(NB, n - j);
-    TEVO_CUDA_CHECK(cudaMemcpy2DAsync(T_, sizeof(cplx) * m, A + (long)j * m, sizeof(cplx) * m, sizeof(cplx) * m, nb,
-                                      cudaMemcpyDeviceToDevice, st));
-    if (j > 0)  // T -= Q(:, 0:j) * L(j:j+nb, 0:j)^H
-      zgemm(st, OP_N, OP_C, m, nb, j, MONE, Q, m, L + j, n, ONE, T_, m);
-    zgemm(st, OP_N, OP_C, m, nb, nb, ONE, T_, m, Linv_ + (size_t)jb * NB * NB, NB, ZERO, Q + (long)j * m, m);
+  // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
+  std::vector<int> bounds;
+  for (int b = 0; b < n; b += NB) bounds.push_back(b);
+  bounds.push_back(n);
+  while (bounds.size() > 2) {
+    std::vector<int> nbnd;
+    size_t k = 0;
+    for (; k + 2 < bounds.size(); k += 2) {
+      const int lo = bounds[k], mid = bounds[k + 1], hi = bounds[k + 2];
+      const int s1 = mid - lo, s2 = hi - mid;
+      // T = B * A^-1 (s2 x s1) ; X21 = -C^-1 * T
+      zgemm(st, OP_N, OP_N, s2, s1, s1, ONE, L + (long)lo * n + mid, n, X + (long)lo * n + lo, n, ZERO, T_, s2);
+      zgemm(st, OP_N, OP_N, s2, s1, s2, MONE, X + (long)mid * n + mid, n, T_, s2, ZERO, X + (long)lo * n + mid, n);
+      nbnd.push_back(lo);
+    }
+    for (; k < bounds.size(); ++k) nbnd.push_back(bounds[k]);
+    bounds = nbnd;
   }
+  // Q = A * inv(L)^H
+  zgemm(st, OP_N, OP_C, m, n, n, ONE, A, m, X, n, ZERO, Q, m);
 }
 
 bool CholQR::factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx* C) {

@@ -34,6 +34,20 @@ struct PanelArgs {
   cplx* taus;
 };
 
+#ifdef TEVO_PANEL_TIMING
+__device__ unsigned long long g_panel_cycles[8];
+#define PT_MARK(slot)                                                     \
+  do {                                                                    \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                            \
+      long long _now = clock64();                                         \
+      atomicAdd(&g_panel_cycles[slot], (unsigned long long)(_now - _t0)); \
+      _t0 = _now;                                                         \
+    }                                                                     \
+  } while (0)
+#else
+#define PT_MARK(slot)
+#endif
+
 __device__ inline cplx ldcg_c(const cplx* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
 // grid-wide barrier for the co-resident (cooperatively launched) panel kernel: one arrival per CTA on a
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   cplx* sv = reinterpret_cast<cplx*>(smraw);  // v (n - p0 entries max)
   __shared__ cplx sred[2 * NT];
   __shared__ cplx pivV[PW], pivW[PW], scw[PW], scv[PW];
-  __shared__ cplx s_tau_prev, s_alpha_prev;
+  __shared__ cplx s_tau_prev, s_alpha_prev, s_yv, s_ypiv;
   __shared__ double sblk[64];
   const int n = a.n, p0 = a.p0, pw = a.pw;
   const int tid = threadIdx.x, rr = tid % RS, cl = tid / RS;
@@ -102,25 +116,51 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   cplx* Yp = a.Y;
   unsigned epoch = 0;
   cplx tau_cur = mk(0, 0);
+#ifdef TEVO_PANEL_TIMING
+  long long _t0 = clock64();
+#endif
 
   for (int i = 0; i <= pw; ++i) {
     const int c = p0 + i;
     // ---------------- phase A ----------------
-    // scalars of column i-1
+    // everything produced by other CTAs that this phase needs is fetched in one round of ld.cg:
+    // the reductions of column i-1 (cw, cv, y^H v), the pivot row c of V / W and the raw y of the pivot row
     if (i > 0) {
       const int ip = i - 1;
-      for (int k = tid; k < ip; k += NT) {
-        scw[k] = mk(__ldcg(&a.acc_cw[2 * (ip * PW + k)]), __ldcg(&a.acc_cw[2 * (ip * PW + k) + 1]));
-        scv[k] = mk(__ldcg(&a.acc_cv[2 * (ip * PW + k)]), __ldcg(&a.acc_cv[2 * (ip * PW + k) + 1]));
+      for (int k = tid; k < i; k += NT) {
+        if (k < ip) {
+          scw[k] = mk(__ldcg(&a.acc_cw[2 * (ip * PW + k)]), __ldcg(&a.acc_cw[2 * (ip * PW + k) + 1]));
+          scv[k] = mk(__ldcg(&a.acc_cv[2 * (ip * PW + k)]), __ldcg(&a.acc_cv[2 * (ip * PW + k) + 1]));
+          if (i < pw) pivW[k] = ldcg_c(&Wp[(long)k * a.ldp + c]);
+        }
+        if (i < pw) pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
+      }
+      if (tid == 0) {
+        s_yv = mk(__ldcg(&a.acc_yv[2 * ip]), __ldcg(&a.acc_yv[2 * ip + 1]));
+        if (i < pw) s_ypiv = ldcg_c(&Yp[(long)ip * a.ldp + c]);
       }
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 32) {  // one warp: Re(cw^H cv) and the pivot-row correction sum
         double re = 0.0;
-        for (int k = 0; k < ip; ++k) re += scw[k].x * scv[k].x + scw[k].y * scv[k].y;  // Re(cw^H cv)
-        const cplx yv = mk(__ldcg(&a.acc_yv[2 * ip]) - 2.0 * re, __ldcg(&a.acc_yv[2 * ip + 1]));
-        const cplx wv = cmul(cconj(tau_cur), yv);  // w^H v = conj(tau) (y^H v - 2 Re(cw^H cv))
-        s_tau_prev = tau_cur;
-        s_alpha_prev = cscale(-0.5, cmul(tau_cur, wv));
+        cplx acc = mk(0, 0);
+        for (int k = tid; k < ip; k += 32) {
+          re += scw[k].x * scv[k].x + scw[k].y * scv[k].y;
+          if (i < pw) {
+            cfma(acc, pivV[k], scw[k]);
+            cfma(acc, pivW[k], scv[k]);
+          }
+        }
+        re = warp_sum(re);
+        acc.x = warp_sum(acc.x);
+        acc.y = warp_sum(acc.y);
+        if (tid == 0) {
+          const cplx yv = mk(s_yv.x - 2.0 * re, s_yv.y);
+          const cplx wv = cmul(cconj(tau_cur), yv);  // w^H v = conj(tau) (y^H v - 2 Re(cw^H cv))
+          const cplx alphap = cscale(-0.5, cmul(tau_cur, wv));
+          s_tau_prev = tau_cur;
+          s_alpha_prev = alphap;
+          if (i < pw) pivW[ip] = cadd(cmul(tau_cur, csub(s_ypiv, acc)), cmul(alphap, pivV[ip]));
+        }
       }
       __syncthreads();
     }
@@ -148,23 +188,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       }
       break;
     }
-    // pivot row c of V and W (columns k < i); the newest column k = i-1 of W is rebuilt from its raw y
-    for (int k = tid; k < i; k += NT) {
-      pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
-      if (k < i - 1) pivW[k] = ldcg_c(&Wp[(long)k * a.ldp + c]);
-    }
-    __syncthreads();
-    if (i > 0 && tid == 0) {
-      const int ip = i - 1;
-      cplx acc = mk(0, 0);
-      for (int k = 0; k < ip; ++k) {
-        cfma(acc, pivV[k], scw[k]);
-        cfma(acc, pivW[k], scv[k]);
-      }
-      const cplx y = ldcg_c(&Yp[(long)ip * a.ldp + c]);
-      pivW[ip] = cadd(cmul(s_tau_prev, csub(y, acc)), cmul(s_alpha_prev, pivV[ip]));
-    }
-    __syncthreads();
+    PT_MARK(0);
     double nrm = 0.0;
     {
       const int ip = i - 1;
@@ -205,9 +229,26 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       block_sum<1>(v1, sblk);
       if (tid == 0 && v1[0] != 0.0) atomicAdd(&a.acc_norm[i], v1[0]);
     }
+    PT_MARK(1);
     epoch += gridDim.x;
     grid_bar(a.bar, epoch);
+    PT_MARK(2);
     // ---------------- phase B: reflector, v, y = A22 v, panel dots ----------------
+    const int nv = n - (c + 1);
+    {
+      // raw column first (independent loads in flight), scalars next, scaling in shared memory last
+      const cplx* colp = a.A + (long)c * a.lda + c + 1;
+      int j = tid;
+      for (; j + 3 * NT < nv; j += 4 * NT) {
+        const cplx x0 = ldcg_c(colp + j), x1 = ldcg_c(colp + j + NT), x2 = ldcg_c(colp + j + 2 * NT),
+                   x3 = ldcg_c(colp + j + 3 * NT);
+        sv[j] = x0;
+        sv[j + NT] = x1;
+        sv[j + 2 * NT] = x2;
+        sv[j + 3 * NT] = x3;
+      }
+      for (; j < nv; j += NT) sv[j] = ldcg_c(colp + j);
+    }
     const double xn2 = __ldcg(&a.acc_norm[i]);
     const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
     double beta;
@@ -229,9 +270,10 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       a.e[c] = beta;
       a.taus[c] = tau;
     }
-    const int nv = n - (c + 1);
-    for (int j = tid; j < nv; j += NT) sv[j] = (j == 0) ? mk(1, 0) : cmul(ldcg_c(&a.A[(long)c * a.lda + c + 1 + j]), scal);
     __syncthreads();
+    for (int j = tid; j < nv; j += NT) sv[j] = (j == 0) ? mk(1, 0) : cmul(sv[j], scal);
+    __syncthreads();
+    PT_MARK(3);
     cplx cwa[PW / 16], cva[PW / 16];
 #pragma unroll
     for (int q = 0; q < PW / 16; ++q) cwa[q] = cva[q] = mk(0, 0);
@@ -243,20 +285,27 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       if (act) {
         const cplx* arow = a.A + r;
         // 8 independent 16-byte loads in flight per thread (the HEMV is latency/L2-bandwidth bound)
-        cplx ac[8];
+        cplx ac[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) ac[u] = mk(0, 0);
+        for (int u = 0; u < 4; ++u) ac[u] = mk(0, 0);
         int j = c + 1 + cl;
-        for (; j + 16 * 7 < n; j += 16 * 8) {
-          cplx av[8];
+        for (; j + 16 * 15 < n; j += 16 * 16) {
+          cplx av[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
+          for (int u = 0; u < 16; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) cfma(ac[u], av[u], sv[j + 16 * u - c - 1]);
+          for (int u = 0; u < 16; ++u) cfma(ac[u & 3], av[u], sv[j + 16 * u - c - 1]);
+        }
+        for (; j + 16 * 3 < n; j += 16 * 4) {
+          cplx av[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cfma(ac[u], av[u], sv[j + 16 * u - c - 1]);
         }
         for (; j < n; j += 16) cfma(ac[0], arow[(long)j * a.lda], sv[j - c - 1]);
 #pragma unroll
-        for (int u = 1; u < 8; ++u) ac[0] = cadd(ac[0], ac[u]);
+        for (int u = 1; u < 4; ++u) ac[0] = cadd(ac[0], ac[u]);
         acc = ac[0];
         const cplx vr = sv[r - c - 1];
 #pragma unroll
@@ -277,6 +326,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         yv1 += y.x * vr.y - y.y * vr.x;
       }
     }
+    PT_MARK(4);
     // reduce the panel dots over the 16 rows of the half-warp, then one atomic per (k, CTA)
 #pragma unroll
     for (int q = 0; q < PW / 16; ++q) {
@@ -304,8 +354,10 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         atomicAdd(&a.acc_yv[2 * i + 1], v2[1]);
       }
     }
+    PT_MARK(5);
     epoch += gridDim.x;
     grid_bar(a.bar, epoch);
+    PT_MARK(6);
   }
   // ---------------- panel epilogue: build [V|W], [W|V], store reflectors into A ----------------
   __syncthreads();
@@ -331,35 +383,36 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   }
 }
 
-// compact-WY T factor of one panel: T(j,j) = tau_j ; T(0:j, j) = -tau_j T(0:j,0:j) (V^H v_j)   (zlarft, forward/columnwise)
-__global__ void build_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ acc_cv,
-                               cplx* __restrict__ T /* PW x PW col-major */) {
-  extern __shared__ __align__(16) unsigned char smT[];
-  cplx(*sT)[PW + 1] = reinterpret_cast<cplx(*)[PW + 1]>(smT);
-  const int k = threadIdx.x;  // row
-  cplx(*sS)[PW + 1] = sT + PW;  // S(l, j) = (V^H v_j)_l
-  for (int j = 0; j < PW; ++j)
-    if (k < PW) {
-      sT[k][j] = mk(0, 0);
-      sS[k][j] = (k < j && j < pw) ? mk(acc_cv[2 * (j * PW + k)], acc_cv[2 * (j * PW + k) + 1]) : mk(0, 0);
-    }
-  __syncthreads();
-  for (int j = 0; j < pw; ++j) {
-    const cplx tj = taus[j];
-    cplx val = mk(0, 0);
-    if (k < j) {
-      cplx acc = mk(0, 0);
-      for (int l = k; l < j; ++l) cfma(acc, sT[k][l], sS[l][j]);
-      val = cscale(-1.0, cmul(tj, acc));
-    } else if (k == j) {
-      val = tj;
-    }
-    __syncthreads();
-    if (k < PW) sT[k][j] = val;
-    __syncthreads();
+// X <- T X for one reflector panel without forming T:  T^-1 = triu(V^H V, 1) + diag(1/tau)  (zlarft identity), so
+// X' solves an upper-triangular system by back substitution; 1/M_jj = tau_j (tau_j = 0: reflector is the identity).
+// S holds (V^H v_l)_j for j < l at S[2*(l*PW + j)] (the panel kernel's acc_cv).  One thread per right-hand side.
+__global__ void __launch_bounds__(128) wy_trsm_kernel(int pw, int k, const cplx* __restrict__ taus,
+                                                      const double* __restrict__ S, cplx* __restrict__ X, long ldx) {
+  extern __shared__ __align__(16) unsigned char smM[];
+  cplx(*sM)[PW + 1] = reinterpret_cast<cplx(*)[PW + 1]>(smM);
+  __shared__ cplx stau[PW];
+  for (int e = threadIdx.x; e < PW * PW; e += blockDim.x) {
+    const int j = e % PW, l = e / PW;
+    sM[j][l] = (j < l && l < pw) ? mk(S[2 * (l * PW + j)], S[2 * (l * PW + j) + 1]) : mk(0, 0);
   }
+  for (int e = threadIdx.x; e < PW; e += blockDim.x) stau[e] = e < pw ? taus[e] : mk(0, 0);
+  __syncthreads();
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= k) return;
+  cplx x[PW];
+  cplx* xc = X + (long)col * ldx;
+#pragma unroll
+  for (int j = 0; j < PW; ++j) x[j] = j < pw ? xc[j] : mk(0, 0);
+#pragma unroll
+  for (int j = PW - 1; j >= 0; --j) {
+    cplx sres = x[j];
+#pragma unroll
+    for (int l = j + 1; l < PW; ++l) sres = csub(sres, cmul(sM[j][l], x[l]));
+    x[j] = cmul(stau[j], sres);
+  }
+#pragma unroll
   for (int j = 0; j < PW; ++j)
-    if (k < PW) T[(long)j * PW + k] = sT[k][j];
+    if (j < pw) xc[j] = x[j];
 }
 
 __global__ void last_diag_kernel(int n, cplx* A, long lda, double* d) {
@@ -380,6 +433,18 @@ __global__ void gather_real_cols_kernel(int n, int k, const double* __restrict__
 
 }  // namespace
 
+#ifdef TEVO_PANEL_TIMING
+extern "C" int tevo_debug_panel_cycles(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_panel_cycles, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_panel_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
 void Heig::init() {
   int dev = 0;
   TEVO_CUDA_CHECK(cudaGetDevice(&dev));
@@ -393,9 +458,10 @@ void Heig::destroy() {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
   Y_ = nullptr;
-  P_ = Q_ = VT_ = nullptr;
+  P_ = Q_ = nullptr;
+  Sall_ = nullptr;
   d_ = e_ = evals_ = Z_ = acc_ = nullptr;
   taus_ = Tblk_ = X_ = part_ = nullptr;
   cap_ = 0;
@@ -406,12 +472,12 @@ void Heig::ensure(int n) {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
   const size_t nn = (size_t)n * n;
   TEVO_CUDA_CHECK(cudaMalloc(&P_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Q_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Y_, sizeof(cplx) * (size_t)n * PW));
-  TEVO_CUDA_CHECK(cudaMalloc(&VT_, sizeof(cplx) * nn));
+  TEVO_CUDA_CHECK(cudaMalloc(&Sall_, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&d_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&e_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * n));
@@ -431,23 +497,24 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   static bool configured = false;
   if (!configured) {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(build_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(2 * sizeof(cplx) * PW * (PW + 1))));
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(cplx) * PW * (PW + 1))));
     configured = true;
   }
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
   double* acc_norm = acc_;
   double* acc_yv = acc_ + PW;
   double* acc_cw = acc_ + 3 * PW;
-  double* acc_cv = acc_ + 3 * PW + 2 * PW * PW;
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
+  TEVO_CUDA_CHECK(cudaMemsetAsync(Sall_, 0, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW), st));
   int p0 = 0;
   while (p0 < n - 1) {
     const int pw = std::min(PW, n - 1 - p0);
     TEVO_CUDA_CHECK(cudaMemsetAsync(acc_, 0, sizeof(double) * (PW + 2 * PW + 4 * PW * PW + 8), st));
     PanelArgs pa;
     pa.n = n; pa.p0 = p0; pa.pw = pw; pa.A = A; pa.lda = lda; pa.P = P_; pa.Q = Q_; pa.Y = Y_; pa.ldp = n;
-    pa.acc_norm = acc_norm; pa.acc_yv = acc_yv; pa.acc_cw = acc_cw; pa.acc_cv = acc_cv;
+    pa.acc_norm = acc_norm; pa.acc_yv = acc_yv; pa.acc_cw = acc_cw;
+    pa.acc_cv = Sall_ + (size_t)(p0 / PW) * 2 * PW * PW;
     pa.bar = reinterpret_cast<unsigned*>(acc_ + PW + 2 * PW + 4 * PW * PW);
     pa.d = d_; pa.e = e_; pa.taus = taus_;
     const int nstrips = (n - p0 + RS - 1) / RS;
@@ -460,12 +527,6 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
       TEVO_LAUNCHED();
     }
     // compact-WY factor and V*T for the back-transformation
-    {
-      ProfScope ps(st, P_TRI_WY);
-      build_T_kernel<<<1, PW, 2 * sizeof(cplx) * PW * (PW + 1), st>>>(pw, taus_ + p0, acc_cv, Tblk_);
-      TEVO_LAUNCHED();
-      zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
-    }
     const int q0 = p0 + pw;
     // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H
     ProfScope ps2(st, P_TRI_HER2K);
@@ -504,14 +565,16 @@ void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ld
     TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * k));
     xcap_ = k;
   }
-  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= (V T) (V^H U)
+  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= V (T (V^H U))
   int last = ((n - 2) / PW) * PW;
   for (int p0 = last; p0 >= 0; p0 -= PW) {
     const int pw = std::min(PW, n - 1 - p0);
     const int rows = n - p0;
     zgemm_splitk(st, OP_C, OP_N, pw, k, rows, ONE, A_ + (long)p0 * lda_ + p0, lda_, U + p0, ldu, ZERO, X_, PW, &part_,
                  &part_cap_);
-    zgemm(st, OP_N, OP_N, rows, k, pw, MONE, VT_ + (long)p0 * n + p0, n, X_, PW, ONE, U + p0, ldu);
+    wy_trsm_kernel<<<(k + 127) / 128, 128, sizeof(cplx) * PW * (PW + 1), st>>>(pw, k, taus_ + p0, Sall_ + (size_t)(p0 / PW) * 2 * PW * PW, X_, PW);
+    TEVO_LAUNCHED();
+    zgemm(st, OP_N, OP_N, rows, k, pw, MONE, A_ + (long)p0 * lda_ + p0, lda_, X_, PW, ONE, U + p0, ldu);
   }
 }
 

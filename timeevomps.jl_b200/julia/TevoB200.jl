@@ -1,0 +1,249 @@
+# TevoB200.jl - thin `ccall` shim that puts libtevo.so (include/tevo.h) behind TimeEvoMPS.jl's own call sites.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: neither Julia nor ITensors.jl exists in the build image (SURVEY.md 0.3), so
+# this file is reviewed, not run.  It is deliberately mechanical: every function is one `ccall` plus the index-order
+# marshalling ITensors needs.  The identical symbols are exercised from Python (timeevomps.jl_b200/_lib.py) by the
+# parity tests, which is what pins their behaviour.
+#
+# Usage inside the reference package (replaces the bodies of src/bondgate.jl:46-63 and the loop body of
+# src/tdvp.jl:56-88; everything else - BondOperator, gates, exp, time_evo_gates, tebd!'s scheduler, the callbacks -
+# stays as it is):
+#
+#     using TevoB200
+#     dpsi = TevoB200.upload(psi)                       # once per tebd!/tdvp! call
+#     spec = TevoB200.apply_gate!(dpsi, G; maxdim=..., cutoff=...)      # instead of apply_gate!(psi, G; ...)
+#     TevoB200.download!(psi, dpsi)                     # before returning / for user callbacks
+module TevoB200
+
+using ITensors
+
+const LIB = get(ENV, "TEVO_LIB", joinpath(@__DIR__, "..", "libtevo.so"))
+
+struct TevoTrunc
+    has_maxdim::Cint
+    maxdim::Cint
+    mindim::Cint
+    has_cutoff::Cint
+    cutoff::Cdouble
+    use_absolute_cutoff::Cint
+    do_rel_cutoff::Cint
+end
+
+struct TevoSpec
+    nkeep::Cint
+    nfull::Cint
+    truncerr::Cdouble
+    entropy::Cdouble
+    sum_all::Cdouble
+    sum_kept::Cdouble
+end
+
+struct TevoKrylov
+    hermitian::Cint
+    tol::Cdouble
+    krylovdim::Cint
+    maxiter::Cint
+end
+
+struct TevoKrylovInfo
+    converged::Cint
+    numops::Cint
+    numiter::Cint
+end
+
+const TEVO_ENOTCONVERGED = 4
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+end
+
+function Ctx(device::Integer=0)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:tevo_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
+    st == 0 || error(unsafe_string(ccall((:tevo_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    c = Ctx(r[])
+    finalizer(x -> ccall((:tevo_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+    return c
+end
+
+check(ctx::Ctx, st) = st == 0 ? nothing :
+    throw(unsafe_string(ccall((:tevo_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h)))
+
+"Device-resident image of an ITensors MPS; keeps the site indices so that download! can rebuild ITensors."
+mutable struct DeviceMPS
+    ctx::Ctx
+    h::Ptr{Cvoid}
+    sites::Vector{<:Index}
+    linktags::Vector{TagSet}
+end
+
+trunc_from(; maxdim=nothing, mindim=1, cutoff=nothing, use_absolute_cutoff=false, absoluteCutoff=false,
+           doRelCutoff=true, kwargs...) =
+    TevoTrunc(maxdim === nothing ? 0 : 1, maxdim === nothing ? 0 : maxdim, mindim,
+              cutoff === nothing ? 0 : 1, cutoff === nothing ? 0.0 : cutoff,
+              (use_absolute_cutoff || absoluteCutoff) ? 1 : 0, doRelCutoff ? 1 : 0)
+
+"Permute site tensor j of `psi` to (left link, site, right link) and return a dense ComplexF64 array."
+function site_array(psi::MPS, j::Int)
+    N = length(psi)
+    s = siteind(psi, j)
+    l = j > 1 ? commonind(psi[j - 1], psi[j]) : nothing
+    r = j < N ? commonind(psi[j], psi[j + 1]) : nothing
+    is = filter(!isnothing, (l, s, r))
+    A = Array{ComplexF64}(array(permute(psi[j], is...)))
+    chil = l === nothing ? 1 : dim(l)
+    chir = r === nothing ? 1 : dim(r)
+    return reshape(A, chil, dim(s), chir)
+end
+
+function upload(psi::MPS; ctx::Ctx=Ctx())
+    N = length(psi)
+    d = dim(siteind(psi, 1))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:tevo_mps_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), ctx.h, N, d, r))
+    dpsi = DeviceMPS(ctx, r[], [siteind(psi, j) for j in 1:N], [tags(linkind(psi, j)) for j in 1:N-1])
+    finalizer(x -> ccall((:tevo_mps_free, LIB), Cint, (Ptr{Cvoid},), x.h), dpsi)
+    for j in 1:N
+        A = site_array(psi, j)
+        GC.@preserve A check(ctx, ccall((:tevo_mps_upload_site, LIB), Cint,
+                                        (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{ComplexF64}),
+                                        dpsi.h, j - 1, size(A, 1), size(A, 3), A))
+    end
+    # ITensors leftlim/rightlim are 1-based "last left-orthogonal"/"first right-orthogonal": subtract 1
+    check(ctx, ccall((:tevo_mps_set_limits, LIB), Cint, (Ptr{Cvoid}, Cint, Cint),
+                     dpsi.h, ITensors.leftlim(psi) - 1, ITensors.rightlim(psi) - 1))
+    return dpsi
+end
+
+"Copy the device state back into `psi` (new link indices are created with the old tags, as replacebond! does)."
+function download!(psi::MPS, dpsi::DeviceMPS)
+    N = length(psi)
+    dims = Vector{Cint}(undef, N - 1)
+    check(dpsi.ctx, ccall((:tevo_mps_bonddims, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), dpsi.h, dims))
+    links = [Index(dims[b], dpsi.linktags[b]) for b in 1:N-1]
+    for j in 1:N
+        chil = j > 1 ? dims[j - 1] : 1
+        chir = j < N ? dims[j] : 1
+        A = Array{ComplexF64}(undef, chil, dim(dpsi.sites[j]), chir)
+        GC.@preserve A check(dpsi.ctx, ccall((:tevo_mps_download_site, LIB), Cint,
+                                             (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Csize_t), dpsi.h, j - 1, A, length(A)))
+        is = filter(!isnothing, (j > 1 ? links[j - 1] : nothing, dpsi.sites[j], j < N ? links[j] : nothing))
+        psi[j] = ITensor(reshape(A, map(dim, is)...), is...)
+    end
+    ll, rl = Ref{Cint}(0), Ref{Cint}(0)
+    check(dpsi.ctx, ccall((:tevo_mps_get_limits, LIB), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Cint}), dpsi.h, ll, rl))
+    ITensors.setleftlim!(psi, ll[] + 1)
+    ITensors.setrightlim!(psi, rl[] + 1)
+    return psi
+end
+
+"Row-major d^2 x d^2 matrix G[(s1',s2'),(s1,s2)] of a BondGate ITensor (primed = out, src/bondgate.jl:24)."
+function gate_matrix(G::ITensor, s1::Index, s2::Index)
+    A = Array{ComplexF64}(array(permute(G, s2', s1', s2, s1)))   # column-major (s2',s1',s2,s1) == row-major ((s1',s2'),(s1,s2))
+    return vec(A)
+end
+
+"apply_gate!(psi, G; kwargs...) (src/bondgate.jl:46-53) on the device state; returns ITensors.Spectrum."
+function apply_gate!(dpsi::DeviceMPS, G::ITensor, b::Int; ortho="left", normalize=true, kwargs...)
+    g = gate_matrix(G, dpsi.sites[b], dpsi.sites[b + 1])
+    tr = Ref(trunc_from(; kwargs...))
+    spec = Ref(TevoSpec(0, 0, 0.0, 0.0, 0.0, 0.0))
+    cap = 4096
+    eigs = Vector{Cdouble}(undef, cap)
+    GC.@preserve g eigs check(dpsi.ctx, ccall((:tevo_apply_gate, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ref{TevoTrunc}, Cint, Cint, Ref{TevoSpec}, Ptr{Cdouble}, Cint),
+        dpsi.h, b - 1, g, tr, ortho == "left" ? 1 : 0, normalize ? 1 : 0, spec, eigs, cap))
+    return ITensors.Spectrum(eigs[1:spec[].nkeep], spec[].truncerr)
+end
+
+"apply_gates!(psi, Gs; reversed, cb, kwargs...) (src/bondgate.jl:55-63): one device call per Trotter layer."
+function apply_gates!(dpsi::DeviceMPS, Gs::Vector{<:Tuple{ITensor,Int}}; reversed=false, cb=nothing, normalize=true, kwargs...)
+    n = length(Gs)
+    bonds = Cint[b - 1 for (_, b) in Gs]
+    gs = reduce(vcat, [gate_matrix(G, dpsi.sites[b], dpsi.sites[b + 1]) for (G, b) in Gs])
+    tr = Ref(trunc_from(; kwargs...))
+    specs = Vector{TevoSpec}(undef, n)
+    stride = 4096
+    eigs = cb === nothing ? Cdouble[] : Vector{Cdouble}(undef, n * stride)
+    GC.@preserve bonds gs specs eigs check(dpsi.ctx, ccall((:tevo_apply_layer, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{ComplexF64}, Cint, Ref{TevoTrunc}, Cint, Cint, Ptr{TevoSpec}, Ptr{Cdouble}, Cint,
+         Cint, Ptr{ComplexF64}, Ptr{ComplexF64}),
+        dpsi.h, n, bonds, gs, reversed ? 1 : 0, tr, normalize ? 1 : 0, 0, specs,
+        cb === nothing ? C_NULL : pointer(eigs), cb === nothing ? 0 : stride, 0, C_NULL, C_NULL))
+    if cb !== nothing
+        for g in (reversed ? (n:-1:1) : (1:n))
+            k = specs[g].nkeep
+            cb(dpsi; bond=Gs[g][2], spec=ITensors.Spectrum(eigs[(g-1)*stride+1:(g-1)*stride+k], specs[g].truncerr))
+        end
+    end
+end
+
+"<O> on sites b and b+1 from theta = psi[b]*psi[b+1] (src/callback.jl:65-73); ops: d x d matrices O[s',s]."
+function measure_bond(dpsi::DeviceMPS, b::Int, ops::Vector{Matrix{ComplexF64}})
+    flat = reduce(vcat, [vec(permutedims(o)) for o in ops])      # row-major
+    out = Vector{ComplexF64}(undef, 2 * length(ops))
+    GC.@preserve flat out check(dpsi.ctx, ccall((:tevo_measure_bond, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), dpsi.h, b - 1, length(ops), flat, out))
+    return reshape(out, 2, length(ops))
+end
+
+# ---- TDVP (src/tdvp.jl:52-88) -------------------------------------------------------------------------
+mutable struct DeviceProjMPO
+    ctx::Ctx
+    hmpo::Ptr{Cvoid}
+    h::Ptr{Cvoid}
+end
+
+function DeviceProjMPO(H::MPO, dpsi::DeviceMPS)
+    N = length(H)
+    d = dim(dpsi.sites[1])
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(dpsi.ctx, ccall((:tevo_mpo_create, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}), dpsi.ctx.h, N, d, r))
+    hm = r[]
+    for j in 1:N
+        s = dpsi.sites[j]
+        l = j > 1 ? commonind(H[j - 1], H[j]) : nothing
+        rr = j < N ? commonind(H[j], H[j + 1]) : nothing
+        is = filter(!isnothing, (l, s', s, rr))
+        W = Array{ComplexF64}(array(permute(H[j], is...)))
+        wl = l === nothing ? 1 : dim(l)
+        wr = rr === nothing ? 1 : dim(rr)
+        GC.@preserve W check(dpsi.ctx, ccall((:tevo_mpo_upload_site, LIB), Cint,
+                                             (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{ComplexF64}), hm, j - 1, wl, wr, W))
+    end
+    e = Ref{Ptr{Cvoid}}(C_NULL)
+    check(dpsi.ctx, ccall((:tevo_env_create, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), hm, e))
+    return DeviceProjMPO(dpsi.ctx, hm, e[])
+end
+
+"Forward two-site step of the sweep (src/tdvp.jl:58-64); throws like :63 when exponentiate does not converge."
+function twosite!(PH::DeviceProjMPO, dpsi::DeviceMPS, b::Int, t::Number; hermitian=true, exp_tol=1e-14, krylovdim=30,
+                  ortho="left", normalize=true, kwargs...)
+    kp = Ref(TevoKrylov(hermitian ? 1 : 0, exp_tol, krylovdim, 100))
+    tr = Ref(trunc_from(; kwargs...))
+    spec = Ref(TevoSpec(0, 0, 0.0, 0.0, 0.0, 0.0))
+    info = Ref(TevoKrylovInfo(0, 0, 0))
+    eigs = Vector{Cdouble}(undef, 4096)
+    tc = ComplexF64(t)
+    st = GC.@preserve eigs ccall((:tevo_tdvp_twosite, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, ComplexF64, Ref{TevoKrylov}, Ref{TevoTrunc}, Cint, Cint, Ref{TevoSpec}, Ptr{Cdouble},
+         Cint, Ref{TevoKrylovInfo}),
+        PH.h, dpsi.h, b - 1, tc, kp, tr, ortho == "left" ? 1 : 0, normalize ? 1 : 0, spec, eigs, 4096, info)
+    st == TEVO_ENOTCONVERGED && throw("exponentiate did not converge")
+    check(dpsi.ctx, st)
+    return ITensors.Spectrum(eigs[1:spec[].nkeep], spec[].truncerr)
+end
+
+"One-site backward step (src/tdvp.jl:77-83)."
+function onesite!(PH::DeviceProjMPO, dpsi::DeviceMPS, i::Int, t::Number; hermitian=true, exp_tol=1e-14, krylovdim=30,
+                  maxiter=100)
+    kp = Ref(TevoKrylov(hermitian ? 1 : 0, exp_tol, krylovdim, maxiter))
+    info = Ref(TevoKrylovInfo(0, 0, 0))
+    st = ccall((:tevo_tdvp_onesite, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Cint, ComplexF64, Ref{TevoKrylov}, Ref{TevoKrylovInfo}),
+               PH.h, dpsi.h, i - 1, ComplexF64(t), kp, info)
+    st == TEVO_ENOTCONVERGED && throw("exponentiate did not converge")
+    check(dpsi.ctx, st)
+end
+
+end # module
