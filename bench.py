@@ -210,7 +210,8 @@ def main():
         if world > 1:
             dist.barrier()
 
-    psi = t.MPS.random(N, chi, seed=rank)
+    from timeevomps_jl_b200 import replicas
+    psi = t.MPS.random(N, chi, seed=replicas.trajectory_seed(rank))
     ctx.synchronize()
     Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
     kw = dict(maxdim=chi, mindim=chi)
@@ -246,10 +247,7 @@ def main():
     prof = t.profile_read(reset=True)
     t.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    ms = replicas.max_over_ranks(ms, dist if world > 1 else None, device="cuda")
     ms_per_step = ms / args.steps
     value = world * 1e3 / ms_per_step
 
@@ -279,10 +277,7 @@ def main():
             del out
         barrier()
         dt_e2e = time.perf_counter() - t0
-        if world > 1:
-            tt = torch.tensor([dt_e2e], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt_e2e = float(tt.item())
+        dt_e2e = replicas.max_over_ranks(dt_e2e, dist if world > 1 else None, device="cuda")
         e2e = {"value": world * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
                "d2h_bytes_per_step": int(nbytes)}
 
@@ -340,6 +335,16 @@ def main():
                                 "ZGEMM peak"},
         "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}, "dominant_phase": dom,
     }
+    try:
+        import ctypes as C
+        from timeevomps_jl_b200._lib import load as _load
+        out = (C.c_double * 11)()
+        _load().tevo_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        _load().tevo_debug_counters(ctx.h, out, 11)
+        line["centre_moves"] = {"cholqr_single_pass": int(out[0]), "cholqr_two_pass": int(out[1]),
+                                "eigen_fallback": int(out[2]), "note": "cumulative since context creation"}
+    except Exception:
+        pass
     if not args.no_cpu:
         line["cpu_baseline"] = CpuArm(args).sample(args.cpu_sample_gates)
     print(json.dumps(line))

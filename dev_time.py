@@ -28,3 +28,10 @@ for it in range(2):
     print({k: (round(v["ms"], 1), v["count"]) for k, v in prof.items()}, "sum", round(tot, 1))
     print("chi", chi, "step", dt, "s;", ng, "gates;", dt / ng * 1e3, "ms/gate; launches", ctx.launch_count() - n0)
 print(abs(t.inner(psi, psi)))
+
+import ctypes as C
+from timeevomps_jl_b200._lib import load
+out=(C.c_double*11)()
+load().tevo_debug_counters.argtypes=[C.c_void_p, C.POINTER(C.c_double), C.c_int]
+load().tevo_debug_counters(ctx.h, out, 11)
+print("cholqr single/double/fail", list(out[:3]), "ratio hist [1,2),[2,4),[4,8),[8,16),[16,64),[64,1e3),[1e3,1e6),fail:", list(out[3:]))

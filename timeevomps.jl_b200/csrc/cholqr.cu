@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "trinv.cuh"
 #include "prof.h"
 #include "zgemm.h"
 
@@ -18,28 +19,35 @@ namespace {
 
 constexpr int NB = 64;
 
-// Cholesky of one nb x nb (nb <= 64) diagonal block of G at (j,j), left-looking, one thread per row: writes L_jj
-// into Lm (lower part) and its inverse into Xm (lower part) at the same position (both column-major, ld),
-// and the extreme pivots into stats[0..1] (stats[0] < 0: breakdown).
-__global__ void __launch_bounds__(64) potrf_block_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
-                                                         cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
+// Cholesky of one nb x nb (nb <= 64) diagonal block of G at (j,j), left-looking, 4 threads per row: writes L_jj into
+// Lm (lower part) and its inverse into Xm (lower part) at the same position (both column-major, ld), and the
+// extreme pivots into stats[0..1] (stats[0] < 0: breakdown).
+__global__ void __launch_bounds__(256) potrf_block_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
+                                                          cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx(*a)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw);  // a[p][i] = L(i,p)   (column p contiguous over rows i)
   cplx(*x)[NB] = a + NB;                                // x[p][c] = inv(L)(p,c)
   __shared__ double s_piv;
   __shared__ int s_fail;
-  const int i = threadIdx.x;
-  for (int p = 0; p < nb; ++p) a[p][i] = (i < nb) ? G[(long)p * ld + i] : mk(0, 0);
-  if (i == 0) s_fail = 0;
+  const int tid = threadIdx.x, i = tid >> 2, part = tid & 3;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int r = e % NB, p = e / NB;
+    a[p][r] = (r < nb && p < nb) ? G[(long)p * ld + r] : mk(r == p ? 1.0 : 0.0, 0.0);
+  }
+  if (tid == 0) s_fail = 0;
   __syncthreads();
   double pmin = 1e300, pmax = 0.0;
   for (int j = 0; j < nb; ++j) {
     cplx sres = mk(0, 0);
     if (i >= j && i < nb) {
-      sres = a[j][i];
-      for (int p = 0; p < j; ++p) sres = csub(sres, cmul(a[p][i], cconj(a[p][j])));
+      for (int p = part; p < j; p += 4) cfma(sres, a[p][i], cconj(a[p][j]));
     }
-    if (i == j) {
+    sres.x += __shfl_xor_sync(0xffffffffu, sres.x, 1);
+    sres.y += __shfl_xor_sync(0xffffffffu, sres.y, 1);
+    sres.x += __shfl_xor_sync(0xffffffffu, sres.x, 2);
+    sres.y += __shfl_xor_sync(0xffffffffu, sres.y, 2);
+    if (i >= j && i < nb) sres = csub(a[j][i], sres);
+    if (i == j && part == 0) {
       const double dkk = sres.x;
       if (!(dkk > 0.0) || !isfinite(dkk)) {
         s_fail = 1;
@@ -53,37 +61,23 @@ __global__ void __launch_bounds__(64) potrf_block_kernel(int nb, const cplx* __r
     const double l = s_piv;
     pmin = fmin(pmin, l);
     pmax = fmax(pmax, l);
-    if (i >= j && i < nb) a[j][i] = (i == j) ? mk(l, 0.0) : cscale(1.0 / l, sres);
+    if (i >= j && i < nb && part == 0) a[j][i] = (i == j) ? mk(l, 0.0) : cscale(1.0 / l, sres);
     __syncthreads();
   }
   if (s_fail) {
-    if (i == 0) {
+    if (tid == 0) {
       stats[0] = -1.0;
       stats[1] = 0.0;
     }
     return;
   }
-  // inverse by forward substitution, thread c owns column c
-  const int c = i;
-  if (c < nb) {
-    for (int r = 0; r < nb; ++r) {
-      if (r < c) {
-        x[r][c] = mk(0, 0);
-        continue;
-      }
-      cplx sres = mk(r == c ? 1.0 : 0.0, 0.0);
-      for (int p = c; p < r; ++p) sres = csub(sres, cmul(a[p][r], x[p][c]));
-      x[r][c] = cscale(1.0 / a[r][r].x, sres);
-    }
+  trinv_lower_256(a, x, nb);
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int r = e % nb, p = e / nb;
+    Lm[(long)p * ld + r] = (r >= p) ? a[p][r] : mk(0, 0);
+    Xm[(long)p * ld + r] = (r >= p) ? x[r][p] : mk(0, 0);
   }
-  __syncthreads();
-  for (int p = 0; p < nb; ++p) {
-    if (i < nb) {
-      Lm[(long)p * ld + i] = (i >= p) ? a[p][i] : mk(0, 0);
-      Xm[(long)p * ld + i] = (i >= p) ? x[i][p] : mk(0, 0);
-    }
-  }
-  if (i == 0) {
+  if (tid == 0) {
     stats[0] = pmin;
     stats[1] = pmax;
   }
@@ -142,7 +136,7 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G_, n);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
-    potrf_block_kernel<<<1, 64, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
+    potrf_block_kernel<<<1, 256, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
                                          d_stats_ + 2 * jb);
     TEVO_LAUNCHED();
     if (rest > 0) {
@@ -190,12 +184,34 @@ bool CholQR::factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx*
       mn = std::min(mn, h_stats_[2 * b]);
       mx = std::max(mx, h_stats_[2 * b + 1]);
     }
+    last_ratio_ = mx / mn;
     return std::isfinite(mx) && mx <= maxratio * mn;
   };
-  pass(st, A, m, n, L1_, Q1_);
-  if (!check(1e6)) return false;
+  pass(st, A, m, n, L1_, Q);
+  {
+    const bool ok1 = check(1e6);
+    const double r = last_ratio_;
+    int bin = !ok1 ? 7 : r < 2 ? 0 : r < 4 ? 1 : r < 8 ? 2 : r < 16 ? 3 : r < 64 ? 4 : r < 1e3 ? 5 : 6;
+    ratio_hist[bin] += 1;
+    if (!ok1) {
+      ++n_fail;
+      return false;
+    }
+  }
+  if (last_ratio_ <= kSinglePassRatio) {
+    // well-conditioned centre tensor (pivot ratio <= 8 => cond^2 * eps far below 1e-12): one pass is enough,
+    // C = L1^H
+    conj_transpose(st, n, n, L1_, n, C, n, true);
+    ++n_single;
+    return true;
+  }
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(Q1_, Q, sizeof(cplx) * (size_t)m * n, cudaMemcpyDeviceToDevice, st));
   pass(st, Q1_, m, n, L2_, Q);
-  if (!check(1.0 + 1e-3)) return false;  // second-pass factor must be ~identity
+  if (!check(1.0 + 1e-3)) {  // second-pass factor must be ~identity
+    ++n_fail;
+    return false;
+  }
+  ++n_double;
   // C = L2^H L1^H = (L1 L2)^H
   const cplx ONE = mk(1, 0), ZERO = mk(0, 0);
   zgemm(st, OP_N, OP_N, n, n, n, ONE, L1_, n, L2_, n, ZERO, G_, n);

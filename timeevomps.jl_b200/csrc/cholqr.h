@@ -17,6 +17,12 @@ class CholQR {
   void pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q);
   cplx *G_ = nullptr, *L1_ = nullptr, *L2_ = nullptr, *Linv_ = nullptr, *T_ = nullptr, *Q1_ = nullptr;
   double *d_stats_ = nullptr, *h_stats_ = nullptr;
+  double last_ratio_ = 0.0;
+ public:
+  long n_single = 0, n_double = 0, n_fail = 0;
+  double ratio_hist[8] = {0};  // counts of pivot ratio in [1,2),[2,4),[4,8),[8,16),[16,64),[64,1e3),[1e3,1e6),fail
+ private:
+  static constexpr double kSinglePassRatio = 8.0;
   int ncap_ = 0;
   size_t mcap_ = 0;
 };

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "prof.h"
+#include "trinv.cuh"
 #include "zgemm.h"
 
 namespace tevo {
@@ -383,36 +384,47 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   }
 }
 
-// X <- T X for one reflector panel without forming T:  T^-1 = triu(V^H V, 1) + diag(1/tau)  (zlarft identity), so
-// X' solves an upper-triangular system by back substitution; 1/M_jj = tau_j (tau_j = 0: reflector is the identity).
-// S holds (V^H v_l)_j for j < l at S[2*(l*PW + j)] (the panel kernel's acc_cv).  One thread per right-hand side.
-__global__ void __launch_bounds__(128) wy_trsm_kernel(int pw, int k, const cplx* __restrict__ taus,
-                                                      const double* __restrict__ S, cplx* __restrict__ X, long ldx) {
-  extern __shared__ __align__(16) unsigned char smM[];
-  cplx(*sM)[PW + 1] = reinterpret_cast<cplx(*)[PW + 1]>(smM);
+// compact-WY T factor of one reflector panel from the identity  T^-1 = triu(V^H V, 1) + diag(1/tau)  (zlarft):
+// the upper-triangular M is inverted in shared memory (as the transpose of a lower-triangular inverse).
+// S holds (V^H v_l)_j for j < l at S[2*(l*PW + j)] (the panel kernel's acc_cv).  tau_j = 0 (identity reflector):
+// row and column j of T are zero.  T is written column-major PW x PW.
+__global__ void __launch_bounds__(256) wy_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ S,
+                                                   cplx* __restrict__ T) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx(*a)[TRB] = reinterpret_cast<cplx(*)[TRB]>(smraw);  // a[p][i] = M^T(i,p) = M(p,i)
+  cplx(*x)[TRB] = a + TRB;
   __shared__ cplx stau[PW];
-  for (int e = threadIdx.x; e < PW * PW; e += blockDim.x) {
-    const int j = e % PW, l = e / PW;
-    sM[j][l] = (j < l && l < pw) ? mk(S[2 * (l * PW + j)], S[2 * (l * PW + j) + 1]) : mk(0, 0);
-  }
-  for (int e = threadIdx.x; e < PW; e += blockDim.x) stau[e] = e < pw ? taus[e] : mk(0, 0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < PW; e += 256) stau[e] = e < pw ? taus[e] : mk(0, 0);
   __syncthreads();
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= k) return;
-  cplx x[PW];
-  cplx* xc = X + (long)col * ldx;
-#pragma unroll
-  for (int j = 0; j < PW; ++j) x[j] = j < pw ? xc[j] : mk(0, 0);
-#pragma unroll
-  for (int j = PW - 1; j >= 0; --j) {
-    cplx sres = x[j];
-#pragma unroll
-    for (int l = j + 1; l < PW; ++l) sres = csub(sres, cmul(sM[j][l], x[l]));
-    x[j] = cmul(stau[j], sres);
+  for (int e = tid; e < PW * PW; e += 256) {
+    const int i = e % PW, p = e / PW;  // M(p,i), upper triangular: p <= i
+    cplx v = mk(0, 0);
+    const bool zp = (p >= pw) || (stau[p].x == 0.0 && stau[p].y == 0.0);
+    const bool zi = (i >= pw) || (stau[i].x == 0.0 && stau[i].y == 0.0);
+    if (p == i) {
+      if (zp) {
+        v = mk(1, 0);
+      } else {
+        const double dn = 1.0 / cabs2(stau[p]);
+        v = mk(stau[p].x * dn, -stau[p].y * dn);  // 1 / tau
+      }
+    } else if (p < i && !zp && !zi) {
+      v = mk(S[2 * (i * PW + p)], S[2 * (i * PW + p) + 1]);
+    }
+    a[p][i] = v;
   }
-#pragma unroll
-  for (int j = 0; j < PW; ++j)
-    if (j < pw) xc[j] = x[j];
+  __syncthreads();
+  trinv_lower_256(a, x, PW);
+  // T(c,p) = inv(M)(c,p) = inv(M^T)(p,c) = x[p][c]
+  for (int e = tid; e < PW * PW; e += 256) {
+    const int c = e % PW, p = e / PW;
+    cplx v = (c <= p) ? x[p][c] : mk(0, 0);
+    const bool zc = (c >= pw) || (stau[c].x == 0.0 && stau[c].y == 0.0);
+    const bool zp = (p >= pw) || (stau[p].x == 0.0 && stau[p].y == 0.0);
+    if (zc || zp) v = mk(0, 0);
+    T[(long)p * PW + c] = v;
+  }
 }
 
 __global__ void last_diag_kernel(int n, cplx* A, long lda, double* d) {
@@ -458,9 +470,9 @@ void Heig::destroy() {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
   Y_ = nullptr;
-  P_ = Q_ = nullptr;
+  P_ = Q_ = VT_ = nullptr;
   Sall_ = nullptr;
   d_ = e_ = evals_ = Z_ = acc_ = nullptr;
   taus_ = Tblk_ = X_ = part_ = nullptr;
@@ -472,12 +484,13 @@ void Heig::ensure(int n) {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
   const size_t nn = (size_t)n * n;
   TEVO_CUDA_CHECK(cudaMalloc(&P_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Q_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Y_, sizeof(cplx) * (size_t)n * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Sall_, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW)));
+  TEVO_CUDA_CHECK(cudaMalloc(&VT_, sizeof(cplx) * nn));
   TEVO_CUDA_CHECK(cudaMalloc(&d_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&e_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * n));
@@ -497,8 +510,8 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   static bool configured = false;
   if (!configured) {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(sizeof(cplx) * PW * (PW + 1))));
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(2 * sizeof(cplx) * TRB * TRB)));
     configured = true;
   }
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
@@ -527,6 +540,12 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
       TEVO_LAUNCHED();
     }
     // compact-WY factor and V*T for the back-transformation
+    {
+      ProfScope ps(st, P_TRI_WY);
+      wy_T_kernel<<<1, 256, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.acc_cv, Tblk_);
+      TEVO_LAUNCHED();
+      zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
+    }
     const int q0 = p0 + pw;
     // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H
     ProfScope ps2(st, P_TRI_HER2K);
@@ -565,16 +584,14 @@ void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ld
     TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * k));
     xcap_ = k;
   }
-  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= V (T (V^H U))
+  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= (V T) (V^H U)
   int last = ((n - 2) / PW) * PW;
   for (int p0 = last; p0 >= 0; p0 -= PW) {
     const int pw = std::min(PW, n - 1 - p0);
     const int rows = n - p0;
     zgemm_splitk(st, OP_C, OP_N, pw, k, rows, ONE, A_ + (long)p0 * lda_ + p0, lda_, U + p0, ldu, ZERO, X_, PW, &part_,
                  &part_cap_);
-    wy_trsm_kernel<<<(k + 127) / 128, 128, sizeof(cplx) * PW * (PW + 1), st>>>(pw, k, taus_ + p0, Sall_ + (size_t)(p0 / PW) * 2 * PW * PW, X_, PW);
-    TEVO_LAUNCHED();
-    zgemm(st, OP_N, OP_N, rows, k, pw, MONE, A_ + (long)p0 * lda_ + p0, lda_, X_, PW, ONE, U + p0, ldu);
+    zgemm(st, OP_N, OP_N, rows, k, pw, MONE, VT_ + (long)p0 * n + p0, n, X_, PW, ONE, U + p0, ldu);
   }
 }
 

@@ -23,7 +23,7 @@ class Heig {
   int cap_ = 0, n_ = 0;
   cplx* A_ = nullptr;
   long lda_ = 0;
-  cplx *P_ = nullptr, *Q_ = nullptr, *Y_ = nullptr, *taus_ = nullptr, *Tblk_ = nullptr, *X_ = nullptr, *part_ = nullptr;
+  cplx *P_ = nullptr, *Q_ = nullptr, *Y_ = nullptr, *VT_ = nullptr, *taus_ = nullptr, *Tblk_ = nullptr, *X_ = nullptr, *part_ = nullptr;
   size_t xcap_ = 0, part_cap_ = 0;
   double *Sall_ = nullptr, *d_ = nullptr, *e_ = nullptr, *evals_ = nullptr, *Z_ = nullptr, *acc_ = nullptr;
 };

@@ -41,6 +41,7 @@ class Split {
     r.swap(pending_release_);
     return r;
   }
+  CholQR& cholqr() { return cholqr_; }
   Heig& heig() { return heig_; }
   int* perm_dev() { return d_perm_; }
   double* sorted_dev() { return d_sorted_; }

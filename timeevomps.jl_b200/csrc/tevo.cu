@@ -1301,3 +1301,14 @@ extern "C" int tevo_profile_read(char* buf, size_t cap, int reset) {
   memcpy(buf, s.c_str(), s.size() + 1);
   return TEVO_OK;
 }
+
+/* development counters: out[0..2] = CholQR single-pass / double-pass / failed, out[3..10] = pivot-ratio histogram */
+extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
+  if (!ctx || !out || n < 11) return TEVO_EINVAL;
+  CholQR& q = ctx->split.cholqr();
+  out[0] = (double)q.n_single;
+  out[1] = (double)q.n_double;
+  out[2] = (double)q.n_fail;
+  for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
+  return TEVO_OK;
+}
