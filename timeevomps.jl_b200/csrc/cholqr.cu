@@ -133,7 +133,11 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   cplx* X = Linv_;  // n x n: inverse of L, assembled below
   TEVO_CUDA_CHECK(cudaMemsetAsync(L, 0, sizeof(cplx) * (size_t)n * n, st));
   TEVO_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(cplx) * (size_t)n * n, st));
-  zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G_, n);
+  {
+    ProfScope ps(st, P_CHOL_GRAM);
+    zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G_, n);
+  }
+  ProfScope* pf = new ProfScope(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
     potrf_block_kernel<<<1, 256, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
@@ -147,6 +151,8 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
             G_ + (long)(j + nb) * n + j + nb, n);
     }
   }
+  delete pf;
+  ProfScope* pi = new ProfScope(st, P_CHOL_INV);
   // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
   std::vector<int> bounds;
   for (int b = 0; b < n; b += NB) bounds.push_back(b);
@@ -165,14 +171,15 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
     for (; k < bounds.size(); ++k) nbnd.push_back(bounds[k]);
     bounds = nbnd;
   }
+  delete pi;
   // Q = A * inv(L)^H
+  ProfScope pq(st, P_CHOL_Q);
   zgemm(st, OP_N, OP_C, m, n, n, ONE, A, m, X, n, ZERO, Q, m);
 }
 
 bool CholQR::factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx* C) {
   if (m < n || n < 1) return false;
   ensure(m, n);
-  ProfScope ps(st, P_HOP_GEMM);
   const int nblk = (n + NB - 1) / NB;
   if (nblk > 64) return false;
   auto check = [&](double maxratio) {

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         }
         if (i < pw) pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
       }
-      if (tid == 0) {
+      if (tid == NT - 1) {  // a thread of another warp than the one that reduces below
         s_yv = mk(__ldcg(&a.acc_yv[2 * ip]), __ldcg(&a.acc_yv[2 * ip + 1]));
         if (i < pw) s_ypiv = ldcg_c(&Yp[(long)ip * a.ldp + c]);
       }
@@ -236,8 +236,10 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     PT_MARK(2);
     // ---------------- phase B: reflector, v, y = A22 v, panel dots ----------------
     const int nv = n - (c + 1);
+    const double xn2 = __ldcg(&a.acc_norm[i]);
+    const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
     {
-      // raw column first (independent loads in flight), scalars next, scaling in shared memory last
+      // scalars and the raw column are fetched in one round of independent loads; scaling happens in shared memory
       const cplx* colp = a.A + (long)c * a.lda + c + 1;
       int j = tid;
       for (; j + 3 * NT < nv; j += 4 * NT) {
@@ -250,8 +252,6 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       }
       for (; j < nv; j += NT) sv[j] = ldcg_c(colp + j);
     }
-    const double xn2 = __ldcg(&a.acc_norm[i]);
-    const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
     double beta;
     cplx tau, scal;
     if (xn2 == 0.0 && alpha.y == 0.0) {
@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     // reduce the panel dots over the 16 rows of the half-warp, then one atomic per (k, CTA)
 #pragma unroll
     for (int q = 0; q < PW / 16; ++q) {
+      if (16 * q >= i) continue;  // no panel column k = cl + 16 q < i in this group (uniform across the CTA)
       double x0 = cwa[q].x, x1 = cwa[q].y, x2 = cva[q].x, x3 = cva[q].y;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) {

@@ -24,6 +24,10 @@ enum ProfId {
   P_KRYLOV_BLAS1,   // Lanczos orthogonalisation / linear combinations
   P_ENV,            // environment updates
   P_MEASURE,        // local expectation values
+  P_CHOL_GRAM,      // CholeskyQR: Gram matrix GEMM
+  P_CHOL_FACTOR,    // CholeskyQR: blocked Cholesky (diagonal blocks + panel/trailing GEMMs)
+  P_CHOL_INV,       // CholeskyQR: triangular inverse assembly
+  P_CHOL_Q,         // CholeskyQR: Q = A L^-H
   P_COUNT
 };
 
