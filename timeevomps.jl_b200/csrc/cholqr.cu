@@ -19,60 +19,30 @@ namespace {
 
 constexpr int NB = 64;
 
-// Cholesky of one nb x nb (nb <= 64) diagonal block of G at (j,j), left-looking, 4 threads per row: writes L_jj into
-// Lm (lower part) and its inverse into Xm (lower part) at the same position (both column-major, ld), and the
-// extreme pivots into stats[0..1] (stats[0] < 0: breakdown).
-__global__ void __launch_bounds__(256) potrf_block_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
-                                                          cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
+// Cholesky of one nb x nb (nb <= 64) diagonal block of G at (j,j) and the inverse of its factor, both in shared
+// memory (right-looking, 1024 threads): writes L_jj into Lm (lower part) and inv(L_jj) into Xm (lower part) at the
+// same position (column-major, ld), and the extreme pivots into stats[0..1] (stats[0] < 0: breakdown).
+__global__ void __launch_bounds__(1024) potrf_block_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
+                                                           cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx(*a)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw);  // a[p][i] = L(i,p)   (column p contiguous over rows i)
   cplx(*x)[NB] = a + NB;                                // x[p][c] = inv(L)(p,c)
-  __shared__ double s_piv;
-  __shared__ int s_fail;
-  const int tid = threadIdx.x, i = tid >> 2, part = tid & 3;
-  for (int e = tid; e < NB * NB; e += 256) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int r = e % NB, p = e / NB;
     a[p][r] = (r < nb && p < nb) ? G[(long)p * ld + r] : mk(r == p ? 1.0 : 0.0, 0.0);
   }
-  if (tid == 0) s_fail = 0;
   __syncthreads();
-  double pmin = 1e300, pmax = 0.0;
-  for (int j = 0; j < nb; ++j) {
-    cplx sres = mk(0, 0);
-    if (i >= j && i < nb) {
-      for (int p = part; p < j; p += 4) cfma(sres, a[p][i], cconj(a[p][j]));
-    }
-    sres.x += __shfl_xor_sync(0xffffffffu, sres.x, 1);
-    sres.y += __shfl_xor_sync(0xffffffffu, sres.y, 1);
-    sres.x += __shfl_xor_sync(0xffffffffu, sres.x, 2);
-    sres.y += __shfl_xor_sync(0xffffffffu, sres.y, 2);
-    if (i >= j && i < nb) sres = csub(a[j][i], sres);
-    if (i == j && part == 0) {
-      const double dkk = sres.x;
-      if (!(dkk > 0.0) || !isfinite(dkk)) {
-        s_fail = 1;
-        s_piv = 1.0;
-      } else {
-        s_piv = sqrt(dkk);
-      }
-    }
-    __syncthreads();
-    if (s_fail) break;
-    const double l = s_piv;
-    pmin = fmin(pmin, l);
-    pmax = fmax(pmax, l);
-    if (i >= j && i < nb && part == 0) a[j][i] = (i == j) ? mk(l, 0.0) : cscale(1.0 / l, sres);
-    __syncthreads();
-  }
-  if (s_fail) {
+  double pmin, pmax;
+  if (!chol_lower_smem(a, nb, pmin, pmax)) {
     if (tid == 0) {
       stats[0] = -1.0;
       stats[1] = 0.0;
     }
     return;
   }
-  trinv_lower_256(a, x, nb);
-  for (int e = tid; e < nb * nb; e += 256) {
+  trinv_lower_smem(a, x, nb);
+  for (int e = tid; e < nb * nb; e += blockDim.x) {
     const int r = e % nb, p = e / nb;
     Lm[(long)p * ld + r] = (r >= p) ? a[p][r] : mk(0, 0);
     Xm[(long)p * ld + r] = (r >= p) ? x[r][p] : mk(0, 0);
@@ -80,6 +50,37 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(int nb, const cplx* __
   if (tid == 0) {
     stats[0] = pmin;
     stats[1] = pmax;
+  }
+}
+
+// E = G - I in place; stats[0] = max |E_ij| (non-negative doubles order like their bit patterns)
+__global__ void gram_minus_identity_kernel(int n, cplx* __restrict__ G, unsigned long long* __restrict__ maxbits) {
+  double m = 0.0;
+  const long total = (long)n * n;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n);
+    const long j = e / n;
+    cplx v = G[e];
+    if (i == j) v.x -= 1.0;
+    G[e] = v;
+    m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(maxbits, (unsigned long long)__double_as_longlong(m));
+}
+
+// S = I - E/2 + (3/8) E2 ,  Sinv = I + E/2 - E2/8      ((I+E)^(-1/2) and (I+E)^(1/2) to second order)
+__global__ void invsqrt_series_kernel(int n, const cplx* __restrict__ E, const cplx* __restrict__ E2, int use_e2,
+                                      cplx* __restrict__ S, cplx* __restrict__ Sinv) {
+  const long total = (long)n * n;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % n);
+    const long j = e / n;
+    const cplx x = E[e];
+    const cplx y = use_e2 ? E2[e] : mk(0, 0);
+    const double d = (i == j) ? 1.0 : 0.0;
+    S[e] = mk(d - 0.5 * x.x + 0.375 * y.x, -0.5 * x.y + 0.375 * y.y);
+    Sinv[e] = mk(d + 0.5 * x.x - 0.125 * y.x, 0.5 * x.y - 0.125 * y.y);
   }
 }
 
@@ -140,7 +141,7 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   ProfScope* pf = new ProfScope(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
-    potrf_block_kernel<<<1, 256, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
+    potrf_block_kernel<<<1, 1024, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
                                          d_stats_ + 2 * jb);
     TEVO_LAUNCHED();
     if (rest > 0) {
@@ -154,16 +155,31 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   delete pf;
   ProfScope* pi = new ProfScope(st, P_CHOL_INV);
   // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
+  // regular part: n = q * NB (+ tail); level s merges blocks [lo, lo+s) and [lo+s, lo+2s), all pairs of a level in
+  // two strided-batched GEMMs.  Irregular leftovers (n not a multiple of 2s) are merged one by one afterwards.
   std::vector<int> bounds;
   for (int b = 0; b < n; b += NB) bounds.push_back(b);
   bounds.push_back(n);
   while (bounds.size() > 2) {
     std::vector<int> nbnd;
     size_t k = 0;
+    // count leading pairs with identical sizes
+    const int s = bounds[1] - bounds[0];
+    int nreg = 0;
+    while (2 * (size_t)nreg + 2 < bounds.size() && bounds[2 * nreg + 1] - bounds[2 * nreg] == s &&
+           bounds[2 * nreg + 2] - bounds[2 * nreg + 1] == s)
+      ++nreg;
+    if (nreg > 0) {
+      const long bs = (long)2 * s * (n + 1);
+      // T_b = B_b * inv(A_b) ; X21_b = -inv(C_b) * T_b
+      zgemm_batched(st, OP_N, OP_N, s, s, s, ONE, L + s, n, bs, X, n, bs, ZERO, T_, s, (long)s * s, nreg);
+      zgemm_batched(st, OP_N, OP_N, s, s, s, MONE, X + (long)s * n + s, n, bs, T_, s, (long)s * s, ZERO, X + s, n, bs, nreg);
+      for (int q = 0; q < nreg; ++q) nbnd.push_back(bounds[2 * q]);
+      k = 2 * (size_t)nreg;
+    }
     for (; k + 2 < bounds.size(); k += 2) {
       const int lo = bounds[k], mid = bounds[k + 1], hi = bounds[k + 2];
       const int s1 = mid - lo, s2 = hi - mid;
-      // T = B * A^-1 (s2 x s1) ; X21 = -C^-1 * T
       zgemm(st, OP_N, OP_N, s2, s1, s1, ONE, L + (long)lo * n + mid, n, X + (long)lo * n + lo, n, ZERO, T_, s2);
       zgemm(st, OP_N, OP_N, s2, s1, s2, MONE, X + (long)mid * n + mid, n, T_, s2, ZERO, X + (long)lo * n + mid, n);
       nbnd.push_back(lo);
@@ -212,15 +228,42 @@ bool CholQR::factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx*
     ++n_single;
     return true;
   }
-  TEVO_CUDA_CHECK(cudaMemcpyAsync(Q1_, Q, sizeof(cplx) * (size_t)m * n, cudaMemcpyDeviceToDevice, st));
-  pass(st, Q1_, m, n, L2_, Q);
-  if (!check(1.0 + 1e-3)) {  // second-pass factor must be ~identity
-    ++n_fail;
-    return false;
-  }
-  ++n_double;
-  // C = L2^H L1^H = (L1 L2)^H
   const cplx ONE = mk(1, 0), ZERO = mk(0, 0);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(Q1_, Q, sizeof(cplx) * (size_t)m * n, cudaMemcpyDeviceToDevice, st));
+  // second pass.  G2 = Q1^H Q1 = I + E: when E is tiny (the usual case) (I+E)^(-1/2) is applied as a series with two
+  // GEMMs instead of a second Cholesky factorisation; otherwise the full CholeskyQR pass is repeated.
+  {
+    ProfScope ps(st, P_CHOL_GRAM);
+    zgemm(st, OP_C, OP_N, n, n, m, ONE, Q1_, m, Q1_, m, ZERO, G_, n);
+  }
+  unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(d_stats_ + 2 * 127);
+  TEVO_CUDA_CHECK(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), st));
+  {
+    const long total = (long)n * n;
+    int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+    gram_minus_identity_kernel<<<blocks, 256, 0, st>>>(n, G_, maxbits);
+    TEVO_LAUNCHED();
+  }
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(h_stats_ + 2 * 127, maxbits, sizeof(double), cudaMemcpyDeviceToHost, st));
+  TEVO_CUDA_CHECK(cudaStreamSynchronize(st));
+  const double emax = h_stats_[2 * 127];
+  if (std::isfinite(emax) && emax * n <= 1e-5) {
+    ProfScope ps(st, P_CHOL_Q);
+    const int use_e2 = (emax * n > 1e-8) ? 1 : 0;
+    if (use_e2) zgemm(st, OP_N, OP_N, n, n, n, ONE, G_, n, G_, n, ZERO, L2_, n);  // E^2
+    {
+      const long total = (long)n * n;
+      int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+      invsqrt_series_kernel<<<blocks, 256, 0, st>>>(n, G_, L2_, use_e2, Linv_, T_);
+      TEVO_LAUNCHED();
+    }
+    zgemm(st, OP_N, OP_N, m, n, n, ONE, Q1_, m, Linv_, n, ZERO, Q, m);  // Q = Q1 (I+E)^(-1/2)
+    zgemm(st, OP_N, OP_C, n, n, n, ONE, T_, n, L1_, n, ZERO, C, n);     // C = (I+E)^(1/2) L1^H
+    ++n_series;
+    return true;
+  }
+  pass(st, Q1_, m, n, L2_, Q);
+  // C = L2^H L1^H = (L1 L2)^H
   zgemm(st, OP_N, OP_N, n, n, n, ONE, L1_, n, L2_, n, ZERO, G_, n);
   conj_transpose(st, n, n, G_, n, C, n, true);
   return true;

@@ -19,7 +19,7 @@ class CholQR {
   double *d_stats_ = nullptr, *h_stats_ = nullptr;
   double last_ratio_ = 0.0;
  public:
-  long n_single = 0, n_double = 0, n_fail = 0;
+  long n_single = 0, n_double = 0, n_fail = 0, n_series = 0;
   double ratio_hist[8] = {0};  // counts of pivot ratio in [1,2),[2,4),[4,8),[8,16),[16,64),[64,1e3),[1e3,1e6),fail
  private:
   static constexpr double kSinglePassRatio = 8.0;

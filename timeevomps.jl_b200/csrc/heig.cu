@@ -389,16 +389,16 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
 // the upper-triangular M is inverted in shared memory (as the transpose of a lower-triangular inverse).
 // S holds (V^H v_l)_j for j < l at S[2*(l*PW + j)] (the panel kernel's acc_cv).  tau_j = 0 (identity reflector):
 // row and column j of T are zero.  T is written column-major PW x PW.
-__global__ void __launch_bounds__(256) wy_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ S,
+__global__ void __launch_bounds__(1024) wy_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ S,
                                                    cplx* __restrict__ T) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx(*a)[TRB] = reinterpret_cast<cplx(*)[TRB]>(smraw);  // a[p][i] = M^T(i,p) = M(p,i)
   cplx(*x)[TRB] = a + TRB;
   __shared__ cplx stau[PW];
   const int tid = threadIdx.x;
-  for (int e = tid; e < PW; e += 256) stau[e] = e < pw ? taus[e] : mk(0, 0);
+  for (int e = tid; e < PW; e += blockDim.x) stau[e] = e < pw ? taus[e] : mk(0, 0);
   __syncthreads();
-  for (int e = tid; e < PW * PW; e += 256) {
+  for (int e = tid; e < PW * PW; e += blockDim.x) {
     const int i = e % PW, p = e / PW;  // M(p,i), upper triangular: p <= i
     cplx v = mk(0, 0);
     const bool zp = (p >= pw) || (stau[p].x == 0.0 && stau[p].y == 0.0);
@@ -416,9 +416,9 @@ __global__ void __launch_bounds__(256) wy_T_kernel(int pw, const cplx* __restric
     a[p][i] = v;
   }
   __syncthreads();
-  trinv_lower_256(a, x, PW);
+  trinv_lower_smem(a, x, PW);
   // T(c,p) = inv(M)(c,p) = inv(M^T)(p,c) = x[p][c]
-  for (int e = tid; e < PW * PW; e += 256) {
+  for (int e = tid; e < PW * PW; e += blockDim.x) {
     const int c = e % PW, p = e / PW;
     cplx v = (c <= p) ? x[p][c] : mk(0, 0);
     const bool zc = (c >= pw) || (stau[c].x == 0.0 && stau[c].y == 0.0);
@@ -543,7 +543,7 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     // compact-WY factor and V*T for the back-transformation
     {
       ProfScope ps(st, P_TRI_WY);
-      wy_T_kernel<<<1, 256, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.acc_cv, Tblk_);
+      wy_T_kernel<<<1, 1024, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.acc_cv, Tblk_);
       TEVO_LAUNCHED();
       zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
     }

@@ -315,7 +315,7 @@ sort_truncate_kernel(const double* __restrict__ lam, int nc, int nfull, TruncPar
 
 __global__ void __launch_bounds__(1024)
 refine_truncate_kernel(const double* __restrict__ lam2, int k1, int nfull, const double* __restrict__ sum_all_dev,
-                       const double* __restrict__ resid2_dev, TruncParams tp, double* __restrict__ sorted,
+                       const double* __restrict__ resid2_dev, int resid_by_difference, TruncParams tp, double* __restrict__ sorted,
                        int* __restrict__ perm, TruncInfo* __restrict__ info, int npow2) {
   extern __shared__ unsigned char sm_raw[];
   double* key = reinterpret_cast<double*>(sm_raw);
@@ -345,7 +345,16 @@ refine_truncate_kernel(const double* __restrict__ lam2, int k1, int nfull, const
   __syncthreads();
   if (threadIdx.x == 0) {
     const double sum_all = *sum_all_dev;
-    double truncerr = (k1 < nfull) ? fmax(*resid2_dev, 0.0) : 0.0;  // absolute weight discarded in stage 1
+    double truncerr = 0.0;  // absolute weight discarded in stage 1
+    if (k1 < nfull) {
+      if (resid_by_difference) {
+        double kept1 = 0.0;
+        for (int i = 0; i < k1; ++i) kept1 += key[i];
+        truncerr = fmax(sum_all - kept1, 0.0);
+      } else {
+        truncerr = fmax(*resid2_dev, 0.0);
+      }
+    }
     int n = k1;
     if (tp.do_truncate && !(key[0] <= 0.0) && k1 > 1) {
       const int mindim = tp.mindim > 1 ? tp.mindim : 1;
@@ -390,7 +399,7 @@ refine_truncate_kernel(const double* __restrict__ lam2, int k1, int nfull, const
 }
 
 void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, const double* sum_all_dev,
-                     const double* resid2_dev, const TruncParams& tp, double* sorted, int* perm, TruncInfo* info) {
+                     const double* resid2_dev, bool resid_by_difference, const TruncParams& tp, double* sorted, int* perm, TruncInfo* info) {
   int npow2 = 1;
   while (npow2 < k1) npow2 <<= 1;
   if (npow2 > 8192) throw TevoError(1, "refine_truncate: more than 8192 singular values not supported");
@@ -401,7 +410,8 @@ void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, con
     configured = true;
   }
   int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;
-  refine_truncate_kernel<<<1, threads, smem, st>>>(lam2, k1, nfull, sum_all_dev, resid2_dev, tp, sorted, perm, info, npow2);
+  refine_truncate_kernel<<<1, threads, smem, st>>>(lam2, k1, nfull, sum_all_dev, resid2_dev, resid_by_difference ? 1 : 0, tp,
+                                                   sorted, perm, info, npow2);
   TEVO_LAUNCHED();
 }
 

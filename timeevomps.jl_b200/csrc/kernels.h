@@ -27,7 +27,8 @@ void sort_truncate(cudaStream_t st, const double* lam, int nc, int nfull, const 
 // stage 2 of the split: sort the Rayleigh-refined weights of the k1 candidate rows, continue upstream's truncate! loop
 // from n = k1 with the accurately known discarded weight *resid2 (absolute), fill the final Spectrum summary
 void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, const double* sum_all_dev,
-                     const double* resid2_dev, const TruncParams& tp, double* sorted, int* perm, TruncInfo* info);
+                     const double* resid2_dev, bool resid_by_difference, const TruncParams& tp, double* sorted, int* perm,
+                     TruncInfo* info);
 void gather_rows(cudaStream_t st, int k, int n, const cplx* src, long lds, const int* perm, cplx* dst, long ldd,
                  const double* norm2);
 void gather_cols(cudaStream_t st, int nr, int k, const cplx* src, long lds, const int* perm, cplx* dst, long ldd,

@@ -278,7 +278,11 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
     conj_transpose(st, n, k1, V, n, R1.p, k1, true);
     colnorm2(st, L1.p, m, m, k1, lam2);
   }
-  if (k1 < nfull) {  // accurately known discarded weight = error of the kept state
+  // discarded weight: when it is a sizeable fraction of the total (stage-1 estimate >= 1e-3 |theta|^2) the difference
+  // |theta|^2 - sum(kept) is accurate to ~1e-13 relative; only small discarded weights need the residual GEMM
+  const bool by_difference = (k1 < nfull) && (res.info.sum_all > 0.0) &&
+                             ((res.info.sum_all - res.info.sum_kept) >= 1e-3 * res.info.sum_all);
+  if (k1 < nfull && !by_difference) {  // accurately known discarded weight = error of the kept state
     ProfScope ps(st, P_RESID);
     cplx* resid = ws(2, (size_t)m * n);
     TEVO_CUDA_CHECK(cudaMemcpyAsync(resid, theta, (size_t)m * n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
@@ -286,7 +290,7 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
     zdotc(st, (long)m * n, resid, resid, d_scal_ + 2);
   }
   // stage 2: upstream's truncate! loop continued on the refined (Rayleigh-quotient) weights
-  refine_truncate(st, lam2, k1, nfull, d_scal_, d_scal_ + 2, tp, d_sorted_, d_perm_, d_info_);
+  refine_truncate(st, lam2, k1, nfull, d_scal_, d_scal_ + 2, by_difference, tp, d_sorted_, d_perm_, d_info_);
   TEVO_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(TruncInfo), cudaMemcpyDeviceToHost, st));
   if (eigs) TEVO_CUDA_CHECK(cudaMemcpyAsync(h_sorted_, d_sorted_, sizeof(double) * k1, cudaMemcpyDeviceToHost, st));
   TEVO_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -1307,7 +1307,7 @@ extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   if (!ctx || !out || n < 11) return TEVO_EINVAL;
   CholQR& q = ctx->split.cholqr();
   out[0] = (double)q.n_single;
-  out[1] = (double)q.n_double;
+  out[1] = (double)(q.n_double + q.n_series);
   out[2] = (double)q.n_fail;
   for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
   return TEVO_OK;

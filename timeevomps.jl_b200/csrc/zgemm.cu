@@ -68,13 +68,18 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
-                  long part_stride) {
-  // split-K: CTA z handles k in [z*Kc, min(Kfull, (z+1)*Kc)) and writes its partial product to C + z*part_stride
-  const int kb = blockIdx.z * Kc;
+                  long part_stride, int nsplit, long bsA, long bsB, long bsC) {
+  // blockIdx.z = batch * nsplit + split.  split-K: split s handles k in [s*Kc, min(Kfull, (s+1)*Kc)) and writes its
+  // partial product to C + s*part_stride; batched: operands of batch b are offset by b*bsA / b*bsB / b*bsC
+  const int zsplit = blockIdx.z % nsplit, zbatch = blockIdx.z / nsplit;
+  A += (long)zbatch * bsA;
+  B += (long)zbatch * bsB;
+  C += (long)zbatch * bsC;
+  const int kb = zsplit * Kc;
   const int K = min(Kfull - kb, Kc);
   A += A_KMAJOR ? (long)kb : (long)kb * lda;
   B += B_KMAJOR ? (long)kb : (long)kb * ldb;
-  C += (long)blockIdx.z * part_stride;
+  C += (long)zsplit * part_stride;
   typedef Tile<BM, A_KMAJOR> TA;
   typedef Tile<BN, B_KMAJOR> TB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +183,8 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
 
 template <bool AK, bool BK_>
 void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
-            long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0) {
+            long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0,
+            int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0) {
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
@@ -188,9 +194,9 @@ void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, lon
                                          (int)smem));
     configured = true;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
   zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc,
-                                                          splits > 1 ? Kc : K, part_stride);
+                                                          splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC);
   TEVO_LAUNCHED();
 }
 
@@ -257,6 +263,23 @@ void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const
     launch<false, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
 }
 
+
+// Strided-batched variant: `batch` independent products with operand strides bsA / bsB / bsC (elements).
+void zgemm_batched(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, long bsA,
+                   const cplx* B, long ldb, long bsB, cplx beta, cplx* C, long ldc, long bsC, int batch) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return;
+  ++g_zgemm_launches;
+  const bool ak = (ta != OP_N), bk = (tb == OP_N);
+  const int ca = (ta == OP_C), cb = (tb == OP_C);
+  if (ak && bk)
+    launch<true, true>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, batch, bsA, bsB, bsC);
+  else if (ak && !bk)
+    launch<true, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, batch, bsA, bsB, bsC);
+  else if (!ak && bk)
+    launch<false, true>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, batch, bsA, bsB, bsC);
+  else
+    launch<false, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, batch, bsA, bsB, bsC);
+}
 
 // Split-K variant for skinny outputs (few CTA tiles, long K): deterministic two-pass (partials + reduce).
 void zgemm_splitk(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
