@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--cpu-sample-gates", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="tebd", choices=["tebd", "tdvp"],
+                    help="tebd: the headline TEBD4 step (default); tdvp: two-site TDVP step (BASELINE config 4 shape)")
     return ap.parse_args()
 
 
@@ -185,11 +187,88 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_tdvp(args):
+    """Secondary workload: one two-site TDVP step (right + left sweep, src/tdvp.jl:54-95) of the XXZ chain at the
+    BASELINE config-4 shape (default N=64 via --nsites, chi=1024, krylovdim=30, exp_tol=1e-12); one independent
+    h value per GPU (replicas).  Reported as an extra JSON line for profiles/, not the headline metric."""
+    import ctypes as C
+    import torch
+    import tevo_b200 as t
+    from timeevomps_jl_b200 import replicas
+    from timeevomps_jl_b200._lib import load as _load
+    rank, world, local = replicas.world()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+    ctx = t.default_ctx()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    N, chi = args.nsites, args.chi
+    hz = replicas.shard_sweep(list(np.linspace(0.0, 1.4, max(world, 1))), rank, world)[0]
+    psi = t.MPS.random(N, chi, seed=replicas.trajectory_seed(rank))
+    H = t.xxz_mpo(N, 1.0, float(hz))
+    kw = dict(maxdim=chi, mindim=chi, exp_tol=1e-12, krylovdim=30)
+    for _ in range(args.warmup):
+        t.tdvp(psi, H, args.dt, args.dt, **kw)
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    out0 = (C.c_double * 12)()
+    _load().tevo_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    _load().tevo_debug_counters(ctx.h, out0, 12)
+    t.profile_enable(True)
+    t.profile_read(reset=True)
+    st = {}
+    n0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        t.tdvp(psi, H, args.dt, args.dt, stats=st, **kw)
+    e1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = replicas.max_over_ranks(e0.elapsed_time(e1), dist, device="cuda")
+    prof = t.profile_read(reset=True)
+    out1 = (C.c_double * 12)()
+    _load().tevo_debug_counters(ctx.h, out1, 12)
+    if rank != 0:
+        return
+    fp64 = {}
+    try:
+        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
+    except Exception:
+        pass
+    zpeak = float(fp64.get("zgemm_tflops_sustained", 36.8))
+    heff_flops = out1[11] - out0[11]
+    hk = prof.get("heff_apply", {"ms": 0.0, "count": 0})
+    ach = heff_flops / (hk["ms"] * 1e-3) / 1e12 if hk["ms"] else None
+    line = {"metric": "tdvp_time_steps_per_sec", "value": world * args.steps * 1e3 / ms, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+            "config": {"workload": "two-site TDVP step (right+left sweep), XXZ S=1/2 chain N=%d chi=%d, w=5 MPO, dt=%g, "
+                                   "krylovdim=30, exp_tol=1e-12, mindim=maxdim=chi" % (N, chi, args.dt),
+                       "parallelism": "1 GPU" if world == 1 else "%d independent field values (replicas)" % world},
+            "gpu_launches": int(ctx.launch_count() - n0), "matvecs": st,
+            "roofline": {"kernel": "zgemm_dmma_kernel (H_eff legs) + mid_contract_kernel", "bound": "tensor",
+                         "achieved": ach, "peak": zpeak, "unit": "TFLOP/s", "frac": (ach / zpeak) if ach else None,
+                         "traffic": None, "peak_source": "measured cuBLAS ZGEMM 4096^3 (profiles/r01_fp64_peaks.json)",
+                         "share_of_step": hk["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0)},
+            "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
+    print(json.dumps(line))
+
+
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "tdvp":
+        run_tdvp(args)
         return
     import torch
     import tevo_b200 as t

@@ -120,3 +120,22 @@ def test_measure_energy(tevo, oracle):
     e_o = oracle.measure_gates(Hg, o)
     e_p = tevo.measure(tevo.gates(tevo.tfi_bondop(N, 1.0, 0.5)), p)
     assert abs(e_o - e_p) <= 1e-12
+
+
+def test_apply_gate_spin_one_sites(tevo, oracle):
+    """d = 3 (spin-1) sites: random two-site unitaries, truncated split vs the oracle (generality row of SURVEY 8(f))."""
+    N, d = 6, 3
+    rng = np.random.default_rng(17)
+    o = oracle.MPS.random(N, 9, d=d, seed=6)
+    p = tevo.MPS.from_tensors(o.A, llim=o.llim, rlim=o.rlim)
+    for b in (2, 3, 0, 4, 1):
+        X = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+        G, _ = np.linalg.qr(X)
+        ospec = oracle.apply_gate(o, oracle.BondGate(G, b), maxdim=7, cutoff=1e-9)
+        spec = tevo.apply_gate(p, tevo.BondGate(G, b), maxdim=7, cutoff=1e-9)
+        assert len(spec) == len(ospec.eigs)
+        np.testing.assert_allclose(spec.eigs, ospec.eigs, rtol=TOL)
+        assert abs(spec.truncerr - ospec.truncerr) <= TOL * ospec.truncerr + 1e-18
+    assert p.bond_dims() == o.bond_dims()
+    ov = oracle.inner(o, oracle.MPS(p.tensors()))
+    assert abs(abs(ov) - 1.0) <= TOL

@@ -909,6 +909,8 @@ extern "C" int tevo_env_position(tevo_env* env, tevo_mps* psi, int pos, int nsit
   TEVO_CATCH
 }
 
+static double g_heff_flops = 0.0;  // algorithmic flops of all H_eff applications (two GEMM legs + operator block)
+
 // H_eff application descriptor at a position (operator block uploaded once, reused by every Krylov matvec)
 struct Heff {
   tevo_ctx* c;
@@ -920,6 +922,11 @@ struct Heff {
   long n;  // vector length
   void apply(const cplx* v, cplx* out) const {
     ProfScope ps(c->stream, P_HEFF);
+    {
+      const double dd0 = (nsite == 2) ? (double)d * d : (double)d;
+      g_heff_flops += 8.0 * ((double)cl * wl * cl * dd0 * cr + (double)cl * cr * (double)P * Q +
+                             (double)cl * dd0 * cr * wr * cr);
+    }
     const int dd = (nsite == 2) ? d * d : d;
     cplx* T1 = c->get_ws(WS_T1, (size_t)cl * wl * dd * cr);
     zgemm(c->stream, OP_N, OP_N, cl * wl, dd * cr, cl, ONE, L, cl * wl, v, cl, ZERO, T1, cl * wl);
@@ -1310,5 +1317,6 @@ extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   out[1] = (double)(q.n_double + q.n_series);
   out[2] = (double)q.n_fail;
   for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
+  if (n >= 12) out[11] = g_heff_flops;
   return TEVO_OK;
 }
