@@ -236,6 +236,18 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     PT_MARK(2);
     // ---------------- phase B: reflector, v, y = A22 v, panel dots ----------------
     const int nv = n - (c + 1);
+    // software pipelining across the scalar phase: the first 8 trailing-matrix loads of this CTA's first strip do not
+    // depend on v, so they are issued now and consumed by the HEMV below
+    cplx pre[8];
+    {
+      const int r0 = p0 + blockIdx.x * RS + rr;
+      const bool act0 = (r0 < n) && (r0 >= c + 1);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = c + 1 + cl + 16 * u;
+        pre[u] = (act0 && j < n) ? a.A[(long)j * a.lda + r0] : mk(0, 0);
+      }
+    }
     const double xn2 = __ldcg(&a.acc_norm[i]);
     const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
     {
@@ -290,6 +302,12 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) ac[u] = mk(0, 0);
         int j = c + 1 + cl;
+        if (s == (int)blockIdx.x) {  // prefetched columns (zero beyond the matrix edge)
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (j + 16 * u < n) cfma(ac[u & 3], pre[u], sv[j + 16 * u - c - 1]);
+          j += 16 * 8;
+        }
         for (; j + 16 * 15 < n; j += 16 * 16) {
           cplx av[16];
 #pragma unroll
