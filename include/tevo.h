@@ -125,6 +125,24 @@ int tevo_measure_bond(tevo_mps* psi, int b, int nops, const tevo_complex* ops, t
  * (src/bondgate.jl:71-79).  h: row-major d^2 x d^2. */
 int tevo_gate_expect(tevo_mps* psi, int b, const tevo_complex* h, tevo_complex* out);
 
+/* ------------------------------------------------ layer-parallel TEBD (multi-GPU building block) ------- */
+/* NOT the reference's algorithm: the reference applies the gates of a layer sequentially with exact centre moves
+ * (src/bondgate.jl:48,55-63).  Chain-segment sharding needs independent gates, i.e. the canonical form
+ * B_j (right-orthonormal) + Schmidt values on every bond with Hastings' inverse-free update.  Identical to the
+ * sequential sweep without truncation; O(discarded weight) apart with it. */
+int tevo_mps_to_bform(tevo_mps* psi);
+int tevo_apply_layer_bform(tevo_mps* psi, int ngates, const int* bonds, const tevo_complex* Gs, const tevo_trunc* trunc,
+                           int normalize, tevo_spec* specs, double* eigs, int eigs_stride);
+int tevo_bform_expect_site(tevo_mps* psi, int j, int nops, const tevo_complex* ops, tevo_complex* out);
+int tevo_mps_get_lambda(tevo_mps* psi, int j, double* host, int cap, int* n_out);
+int tevo_mps_set_lambda(tevo_mps* psi, int j, int n, const double* host);
+int tevo_mps_mark_bform(tevo_mps* psi, int on);
+/* raw device views / device-side setters for the NCCL peer-to-peer exchange of boundary tensors */
+int tevo_mps_site_devptr(tevo_mps* psi, int j, void** ptr, int* chil, int* chir);
+int tevo_mps_lambda_devptr(tevo_mps* psi, int j, void** ptr, int* n);
+int tevo_mps_set_site_from_device(tevo_mps* psi, int j, int chil, int chir, const void* dev_site);
+int tevo_mps_set_lambda_from_device(tevo_mps* psi, int j, int n, const void* dev_lam);
+
 /* ---------------------------------------------------------------- TDVP ---------------------------------- */
 int tevo_mpo_create(tevo_ctx* ctx, int nsites, int d, tevo_mpo** out);
 int tevo_mpo_free(tevo_mpo* H);

@@ -959,3 +959,128 @@ def free_fermions_densities(N: int, dt: float, tf: float) -> List[np.ndarray]:
 def tfi_exact_critical_energy(N: int) -> float:
     """test/test_tebd.jl:68."""
     return 0.25 - 0.25 / math.sin(math.pi / (4 * N + 2))
+
+
+# --------------------------------------------------------------------------------------
+# Layer-parallel TEBD (Vidal / Hastings form)  -  NOT the reference's algorithm.
+#
+# The reference applies the gates of a layer sequentially with exact re-canonicalisation between gates
+# (src/bondgate.jl:48,55-63).  Sharding a layer over GPUs needs gates that are independent of each other; the
+# standard way is the canonical form B_j (right-orthonormal) + Schmidt values Lambda_j on every bond, updated with
+# Hastings' inverse-free rule.  Without truncation it is the same state as the sequential sweep; with truncation the
+# two differ at the order of the discarded weight (SURVEY.md 0.6, 8(e)).  This restatement is the checker of the
+# CUDA layer-parallel / multi-GPU mode.
+# --------------------------------------------------------------------------------------
+class BForm:
+    """B[j]: (chi_j, d, chi_{j+1}) right-orthonormal; lam[j]: Schmidt values on the bond left of site j
+    (lam[0] = lam[N] = [1])."""
+
+    def __init__(self, B, lam):
+        self.B = [np.asarray(b, dtype=complex).copy() for b in B]
+        self.lam = [np.asarray(l, dtype=float).copy() for l in lam]
+
+    @property
+    def N(self):
+        return len(self.B)
+
+    def copy(self):
+        return BForm(self.B, self.lam)
+
+    def to_mps(self) -> "MPS":
+        """A B-form state is a right-canonical MPS with its centre on site 0."""
+        return MPS(self.B, llim=-1, rlim=1)
+
+    def bond_dims(self):
+        return [self.B[j].shape[2] for j in range(self.N - 1)]
+
+    def expect_site(self, op, j) -> complex:
+        O = op_matrix(op) if isinstance(op, str) else op
+        T = self.lam[j][:, None, None] * self.B[j]
+        return complex(np.einsum("atb,ts,asb->", T.conj(), O, T, optimize=True))
+
+    def expect_all(self, op) -> np.ndarray:
+        return np.array([self.expect_site(op, j).real for j in range(self.N)])
+
+    def entropies(self):
+        out = []
+        for j in range(1, self.N):
+            p = self.lam[j] ** 2
+            p = p[p > 1e-13]
+            out.append(float(-np.sum(p * np.log(p))))
+        return out
+
+
+def to_bform(psi: MPS) -> BForm:
+    """Left-canonicalise, then sweep leftwards with SVDs: B_j = V^dagger (right factor), lam_j = S."""
+    p = psi.copy()
+    N = p.N
+    p.orthogonalize(N - 1)
+    p.A[N - 1] = p.A[N - 1] / np.linalg.norm(p.A[N - 1])
+    B = [None] * N
+    lam = [None] * (N + 1)
+    lam[N] = np.ones(1)
+    C = p.A[N - 1]
+    for j in range(N - 1, 0, -1):
+        l, d, r = C.shape
+        U, S, Vh = np.linalg.svd(C.reshape(l, d * r), full_matrices=False)
+        k = len(S)
+        B[j] = Vh.reshape(k, d, r)
+        lam[j] = S.copy()
+        C = np.tensordot(p.A[j - 1], U * S[None, :], axes=(2, 0))
+    B[0] = C
+    lam[0] = np.ones(1)
+    return BForm(B, lam)
+
+
+def apply_gate_bform(st: BForm, g: BondGate, *, normalize=True, maxdim=None, mindim=1, cutoff=None,
+                     use_absolute_cutoff=False, do_rel_cutoff=True) -> Spectrum:
+    """Hastings' inverse-free two-site update of bond b in B-form."""
+    b = g.b
+    C = np.tensordot(st.B[b], st.B[b + 1], axes=(2, 0))  # (l, s1, s2, r)
+    l, d1, d2, r = C.shape
+    C = np.tensordot(g.G.reshape(d1, d2, d1, d2), C, axes=([2, 3], [1, 2])).transpose(2, 0, 1, 3)
+    theta = st.lam[b][:, None, None, None] * C
+    U, S, Vh = np.linalg.svd(theta.reshape(l * d1, d2 * r), full_matrices=False)
+    P = S ** 2
+    if maxdim is not None or cutoff is not None:
+        nkeep, truncerr = truncate_probs(P, maxdim=maxdim, mindim=mindim, cutoff=0.0 if cutoff is None else cutoff,
+                                         use_absolute_cutoff=use_absolute_cutoff, do_rel_cutoff=do_rel_cutoff)
+    else:
+        nkeep, truncerr = len(P), 0.0
+    S, Vh, P = S[:nkeep], Vh[:nkeep], P[:nkeep]
+    nrm = np.sqrt(np.sum(P)) if normalize else 1.0
+    st.B[b + 1] = Vh.reshape(nkeep, d2, r)
+    st.B[b] = (C.reshape(l * d1, d2 * r) @ Vh.conj().T).reshape(l, d1, nkeep) / nrm
+    st.lam[b + 1] = S / nrm
+    return Spectrum(P.copy(), float(truncerr))
+
+
+def apply_layer_bform(st: BForm, Gs: Sequence[BondGate], **kw) -> List[Spectrum]:
+    """All gates of one even/odd layer act on disjoint bonds and only read the Schmidt values of bonds the layer does
+    not touch, so the order is irrelevant (that is what makes the layer shardable)."""
+    return [apply_gate_bform(st, g, **kw) for g in Gs]
+
+
+def tebd_parallel(st: BForm, H, dt, tf, alg=None, **kw) -> BForm:
+    """The schedule of tebd! (src/tebd.jl:113-177, no callbacks) driving layer-parallel updates."""
+    alg = TEBD2() if alg is None else alg
+    if isinstance(H, BondOperator):
+        H = H.gates()
+    nsteps = _nsteps(tf, dt)
+    Ustart, Us, Uend = time_evo_gates(dt, H, alg)
+    nbunch = nsteps
+    if len(Ustart) == 0 and len(Uend) == 0:
+        nbunch += 1
+    step = 0
+    while step < nsteps:
+        for U in Ustart:
+            apply_layer_bform(st, U, **kw)
+        for _ in range(nbunch - 1):
+            for U in Us:
+                apply_layer_bform(st, U, **kw)
+            step += 1
+        for U in Uend:
+            apply_layer_bform(st, U, **kw)
+        if len(Uend) > 0:
+            step += 1
+    return st

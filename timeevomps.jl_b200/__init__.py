@@ -12,7 +12,8 @@ from .bondop import (BondOperator, BondGate, SiteTerm, BondTerm, GateList, add, 
                      bondterms, coeff, exp, expm, measure, tfi_bondop, xxz_bondop)
 from .callback import (TEvoCallback, NoTEvoCallback, LocalMeasurementCallback, SpecCallback, measurement_ts,
                        measurements)
-from .tebd import TEBDalg, TEBD2, TEBD2Sweep, TEBD4, apply_gate, apply_gates, time_evo_gates, tebd
+from .tebd import (TEBDalg, TEBD2, TEBD2Sweep, TEBD4, apply_gate, apply_gates, time_evo_gates, tebd,
+                   apply_gates_parallel, tebd_parallel)
 from .tdvp import TDVP2, ProjMPO, sweepnext, tdvp
 
 __all__ = [n for n in dir() if not n.startswith("_")]

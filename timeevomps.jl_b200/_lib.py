@@ -90,6 +90,16 @@ PROTOTYPES = {
     "tevo_test_split": (_I, [_P, _I, _I, _CP, C.POINTER(tevo_trunc), _I, _I, C.POINTER(tevo_spec), _DP, _I, _CP, _CP,
                              _I]),
     "tevo_test_heig": (_I, [_P, _I, _CP, _DP, _CP]),
+    "tevo_mps_to_bform": (_I, [_P]),
+    "tevo_apply_layer_bform": (_I, [_P, _I, _IP, _CP, C.POINTER(tevo_trunc), _I, C.POINTER(tevo_spec), _DP, _I]),
+    "tevo_bform_expect_site": (_I, [_P, _I, _I, _CP, _CP]),
+    "tevo_mps_get_lambda": (_I, [_P, _I, _DP, _I, _IP]),
+    "tevo_mps_set_lambda": (_I, [_P, _I, _I, _DP]),
+    "tevo_mps_mark_bform": (_I, [_P, _I]),
+    "tevo_mps_site_devptr": (_I, [_P, _I, _PP, _IP, _IP]),
+    "tevo_mps_lambda_devptr": (_I, [_P, _I, _PP, _IP]),
+    "tevo_mps_set_site_from_device": (_I, [_P, _I, _I, _I, _P]),
+    "tevo_mps_set_lambda_from_device": (_I, [_P, _I, _I, _P]),
     "tevo_profile_enable": (_I, [_I]),
     "tevo_profile_read": (_I, [C.c_char_p, C.c_size_t, _I]),
 }

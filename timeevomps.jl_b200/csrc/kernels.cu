@@ -739,4 +739,83 @@ void copy_scale(cudaStream_t st, long n, double s, const cplx* in, cplx* out) {
   TEVO_LAUNCHED();
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// B-form (layer-parallel TEBD) helpers
+// ------------------------------------------------------------------------------------------------
+// out(r, c) = lam[r % chil] * in(r, c)     (rows are (l, s) with l fastest)
+__global__ void scale_rows_kernel(int m, long n, int chil, const double* __restrict__ lam, const cplx* __restrict__ in,
+                                  cplx* __restrict__ out) {
+  const long total = (long)m * n;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(e % m);
+    out[e] = cscale(lam[r % chil], in[e]);
+  }
+}
+void scale_rows(cudaStream_t st, int m, long n, int chil, const double* lam, const cplx* in, cplx* out) {
+  if (m <= 0 || n <= 0) return;
+  scale_rows_kernel<<<grid_for((long)m * n), 256, 0, st>>>(m, n, chil, lam, in, out);
+  TEVO_LAUNCHED();
+}
+
+// out[i] = sqrt(max(in[i], 0) / (*denom))   (denom == nullptr: 1)
+__global__ void sqrt_scaled_kernel(int n, const double* __restrict__ in, const double* __restrict__ denom,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double dn = denom ? *denom : 1.0;
+  if (!(dn > 0.0)) dn = 1.0;
+  out[i] = sqrt(fmax(in[i], 0.0) / dn);
+}
+void sqrt_scaled(cudaStream_t st, int n, const double* in, const double* denom, double* out) {
+  if (n <= 0) return;
+  sqrt_scaled_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, in, denom, out);
+  TEVO_LAUNCHED();
+}
+
+// <T|O_o|T> with T(l,s,r) = lam[l] * B(l,s,r); out: nops complex (zeroed here)
+template <int D>
+__global__ void expect1_kernel(const cplx* __restrict__ B, int chil, int chir, const double* __restrict__ lam, int nops,
+                               const cplx* __restrict__ ops, double* __restrict__ out) {
+  __shared__ double red[2 * 32];
+  const long total = (long)chil * chir;
+  for (int o = 0; o < nops; ++o) {
+    const cplx* O = ops + (long)o * D * D;
+    double v[2] = {0, 0};
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+      const int l = (int)(e % chil);
+      const long r = e / chil;
+      const double w = lam[l] * lam[l];
+      cplx t[D];
+#pragma unroll
+      for (int s = 0; s < D; ++s) t[s] = B[l + (long)chil * (s + D * r)];
+      cplx acc = mk(0, 0);
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = 0; b < D; ++b) cfma_conj(acc, t[a], cmul(O[a * D + b], t[b]));
+      v[0] += w * acc.x;
+      v[1] += w * acc.y;
+    }
+    block_sum<2>(v, red);
+    if (threadIdx.x == 0) {
+      atomicAdd(out + 2 * o, v[0]);
+      atomicAdd(out + 2 * o + 1, v[1]);
+    }
+    __syncthreads();
+  }
+}
+void expect1(cudaStream_t st, const cplx* B, int chil, int d, int chir, const double* lam, int nops, const cplx* ops_dev,
+             double* out_dev) {
+  TEVO_CUDA_CHECK(cudaMemsetAsync(out_dev, 0, sizeof(double) * 2 * nops, st));
+  const int grid = grid_for((long)chil * chir, 256, 148 * 2);
+  switch (d) {
+    case 2: expect1_kernel<2><<<grid, 256, 0, st>>>(B, chil, chir, lam, nops, ops_dev, out_dev); break;
+    case 3: expect1_kernel<3><<<grid, 256, 0, st>>>(B, chil, chir, lam, nops, ops_dev, out_dev); break;
+    case 4: expect1_kernel<4><<<grid, 256, 0, st>>>(B, chil, chir, lam, nops, ops_dev, out_dev); break;
+    default: throw TevoError(1, "expect1: physical dimension d must be 2, 3 or 4");
+  }
+  TEVO_LAUNCHED();
+}
+
 }  // namespace tevo

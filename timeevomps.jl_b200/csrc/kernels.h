@@ -46,5 +46,9 @@ void multi_dotc(cudaStream_t st, long n, int k, const cplx* V, long ldv, const c
 void multi_axpy_sub(cudaStream_t st, long n, int k, const cplx* V, long ldv, const double* h_dev, cplx* r);
 void lincomb(cudaStream_t st, long n, int k, const cplx* V, long ldv, const double* y_dev, double scale, cplx* out);
 void copy_scale(cudaStream_t st, long n, double s, const cplx* in, cplx* out);
+void scale_rows(cudaStream_t st, int m, long n, int chil, const double* lam, const cplx* in, cplx* out);
+void sqrt_scaled(cudaStream_t st, int n, const double* in, const double* denom, double* out);
+void expect1(cudaStream_t st, const cplx* B, int chil, int d, int chir, const double* lam, int nops, const cplx* ops_dev,
+             double* out_dev);
 
 }  // namespace tevo

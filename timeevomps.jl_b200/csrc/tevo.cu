@@ -103,6 +103,10 @@ struct tevo_mps {
   std::vector<DevBuf> site;
   std::vector<int> chi;  // N+1
   int llim, rlim;
+  // layer-parallel (B-form) mode: Schmidt values on the bond left of site j (device), valid when bform
+  bool bform = false;
+  std::vector<double*> lam;  // N+1 device arrays (lam[j] has chi[j] entries)
+  std::vector<int> lam_cap;
 };
 
 struct tevo_mpo {
@@ -193,6 +197,7 @@ static void set_site(tevo_mps* psi, int j, DevBuf nb) {
 // centre j -> j+1 (QR-equivalent hop of orthogonalize!; here an untruncated split U * (S V^+))
 static void hop_right(tevo_mps* psi, int j) {
   tevo_ctx* c = psi->ctx;
+  psi->bform = false;
   const int d = psi->d, m = psi->chi[j] * d, n = psi->chi[j + 1];
   SplitResult r = c->split.ortho_factor(c->stream, psi->site[j].p, m, n, /*left=*/true,
                                         [&](size_t ne) { return c->alloc(ne); });
@@ -211,6 +216,7 @@ static void hop_right(tevo_mps* psi, int j) {
 // centre j -> j-1
 static void hop_left(tevo_mps* psi, int j) {
   tevo_ctx* c = psi->ctx;
+  psi->bform = false;
   const int d = psi->d, m = psi->chi[j], n = d * psi->chi[j + 1];
   SplitResult r = c->split.ortho_factor(c->stream, psi->site[j].p, m, n, /*left=*/false,
                                         [&](size_t ne) { return c->alloc(ne); });
@@ -267,6 +273,7 @@ static cplx* form_theta(tevo_mps* psi, int b, int slot = WS_THETA) {
 static TruncInfo replace_bond(tevo_mps* psi, int b, const cplx* theta, bool left, const TruncParams& tp, bool normalize,
                               double* eigs, int eigs_cap) {
   tevo_ctx* c = psi->ctx;
+  psi->bform = false;
   const int d = psi->d, m = psi->chi[b] * d, n = d * psi->chi[b + 2];
   SplitResult r = c->split.run(c->stream, theta, m, n, left, tp, normalize, eigs, eigs_cap,
                                [&](size_t ne) { return c->alloc(ne); });
@@ -405,6 +412,8 @@ extern "C" int tevo_mps_create(tevo_ctx* ctx, int nsites, int d, tevo_mps** out)
 extern "C" int tevo_mps_free(tevo_mps* psi) {
   if (!psi) return TEVO_OK;
   for (auto& b : psi->site) psi->ctx->release(b);
+  for (auto p : psi->lam)
+    if (p) cudaFree(p);
   delete psi;
   return TEVO_OK;
 }
@@ -426,6 +435,18 @@ extern "C" int tevo_mps_copy(tevo_mps* src, tevo_mps** out) {
     p->site[j] = c->alloc(ne);
     TEVO_CUDA_CHECK(cudaMemcpyAsync(p->site[j].p, src->site[j].p, ne * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
   }
+  p->bform = src->bform;
+  if (!src->lam.empty()) {
+    p->lam.assign(src->N + 1, nullptr);
+    p->lam_cap.assign(src->N + 1, 0);
+    for (int j = 0; j <= src->N; ++j) {
+      if (!src->lam[j]) continue;
+      const int n = src->chi[j];
+      TEVO_CUDA_CHECK(cudaMalloc(&p->lam[j], sizeof(double) * n));
+      p->lam_cap[j] = n;
+      TEVO_CUDA_CHECK(cudaMemcpyAsync(p->lam[j], src->lam[j], sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  }
   *out = p;
   TEVO_CATCH
 }
@@ -442,6 +463,7 @@ extern "C" int tevo_mps_upload_site(tevo_mps* psi, int j, int chil, int chir, co
   set_site(psi, j, nb);
   psi->chi[j] = chil;
   psi->chi[j + 1] = chir;
+  psi->bform = false;
   // unknown gauge after an upload
   if (psi->llim >= j) psi->llim = j - 1;
   if (psi->rlim <= j) psi->rlim = j + 1;
@@ -1319,4 +1341,200 @@ extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
   if (n >= 12) out[11] = g_heff_flops;
   return TEVO_OK;
+}
+
+// =====================================================================================================
+// Layer-parallel TEBD in canonical B-form (Vidal / Hastings).  NOT the reference's sequential algorithm: the gates of
+// a layer are independent here, which is what chain-segment sharding over GPUs needs; identical to
+// the sequential sweep without truncation, O(discarded weight) apart with it.
+// =====================================================================================================
+static double* lam_buf(tevo_mps* psi, int j, int n) {
+  if (psi->lam.empty()) {
+    psi->lam.assign(psi->N + 1, nullptr);
+    psi->lam_cap.assign(psi->N + 1, 0);
+  }
+  if (psi->lam_cap[j] < n) {
+    if (psi->lam[j]) TEVO_CUDA_CHECK(cudaFree(psi->lam[j]));
+    psi->lam[j] = nullptr;
+    int want = n + n / 4 + 8;
+    TEVO_CUDA_CHECK(cudaMalloc(&psi->lam[j], sizeof(double) * want));
+    psi->lam_cap[j] = want;
+  }
+  return psi->lam[j];
+}
+
+static void set_lam_ones(tevo_mps* psi, int j) {
+  double one = 1.0;
+  double* p = lam_buf(psi, j, 1);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(p, &one, sizeof(double), cudaMemcpyHostToDevice, psi->ctx->stream));
+}
+
+/* psi -> right-orthonormal B tensors + Schmidt values on every bond (centre ends on site 0) */
+extern "C" int tevo_mps_to_bform(tevo_mps* psi) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi, "null");
+  tevo_ctx* c = psi->ctx;
+  const int N = psi->N, d = psi->d;
+  orthogonalize(psi, N - 1);
+  {
+    size_t ne = (size_t)psi->chi[N - 1] * d * psi->chi[N];
+    zdotc(c->stream, (long)ne, psi->site[N - 1].p, psi->site[N - 1].p, c->d_scal);
+    zscal_rsqrt(c->stream, (long)ne, c->d_scal, psi->site[N - 1].p);
+  }
+  TruncParams tp = to_params(nullptr);
+  for (int j = N - 1; j >= 1; --j) {
+    const int m = psi->chi[j], n = d * psi->chi[j + 1];
+    SplitResult r = c->split.run(c->stream, psi->site[j].p, m, n, /*left=*/false, tp, false, nullptr, 0,
+                                 [&](size_t ne) { return c->alloc(ne); });
+    const int k = r.k, m2 = psi->chi[j - 1] * d;
+    sqrt_scaled(c->stream, k, c->split.sorted_dev(), nullptr, lam_buf(psi, j, k));
+    DevBuf nb = c->alloc((size_t)m2 * k);
+    zgemm(c->stream, OP_N, OP_N, m2, k, m, ONE, psi->site[j - 1].p, m2, r.L.p, m, ZERO, nb.p, m2);
+    c->release(r.L);
+    set_site(psi, j, r.R);
+    set_site(psi, j - 1, nb);
+    psi->chi[j] = k;
+  }
+  set_lam_ones(psi, 0);
+  set_lam_ones(psi, N);
+  psi->llim = -1;
+  psi->rlim = 1;
+  psi->bform = true;
+  TEVO_CATCH
+}
+
+/* Hastings' inverse-free update of every gate of one layer; the gates are independent (any order). */
+extern "C" int tevo_apply_layer_bform(tevo_mps* psi, int ngates, const int* bonds, const tevo_complex* Gs,
+                                      const tevo_trunc* trunc, int normalize, tevo_spec* specs, double* eigs,
+                                      int eigs_stride) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && (ngates == 0 || (bonds && Gs)), "tevo_apply_layer_bform: null argument");
+  require(psi->bform, "tevo_apply_layer_bform: state is not in B-form (call tevo_mps_to_bform)");
+  tevo_ctx* c = psi->ctx;
+  const int d = psi->d, d4 = d * d * d * d;
+  cplx* dG = (cplx*)c->small(sizeof(cplx) * d4 * (size_t)std::max(ngates, 1));
+  if (ngates) upload_small(c, dG, Gs, sizeof(cplx) * d4 * (size_t)ngates);
+  const TruncParams tp = to_params(trunc);
+  for (int g = 0; g < ngates; ++g) {
+    const int b = bonds[g];
+    require(b >= 0 && b < psi->N - 1, "tevo_apply_layer_bform: bond out of range");
+    const int chil = psi->chi[b], m = chil * d, kk = psi->chi[b + 1], n = d * psi->chi[b + 2];
+    cplx* C = c->get_ws(WS_THETA, (size_t)m * n);
+    {
+      ProfScope ps(c->stream, P_THETA);
+      zgemm(c->stream, OP_N, OP_N, m, n, kk, ONE, psi->site[b].p, m, psi->site[b + 1].p, kk, ZERO, C, m);
+    }
+    gate_apply(c->stream, C, chil, d, psi->chi[b + 2], dG + (size_t)g * d4);
+    cplx* th = c->get_ws(WS_T1, (size_t)m * n);
+    scale_rows(c->stream, m, n, chil, psi->lam[b], C, th);
+    SplitResult r = c->split.run(c->stream, th, m, n, /*left=*/false, tp, false, eigs ? eigs + (size_t)g * eigs_stride : nullptr,
+                                 eigs ? eigs_stride : 0, [&](size_t ne) { return c->alloc(ne); });
+    const int k = r.k;
+    DevBuf nb = c->alloc((size_t)m * k);
+    {
+      ProfScope ps(c->stream, P_SPLIT_GEMM);
+      zgemm(c->stream, OP_N, OP_C, m, k, n, ONE, C, m, r.R.p, k, ZERO, nb.p, m);  // B'_b = C V
+    }
+    const double* denom = normalize ? &c->split.info_dev()->sum_kept : nullptr;
+    if (normalize) zscal_rsqrt(c->stream, (long)m * k, denom, nb.p);
+    sqrt_scaled(c->stream, k, c->split.sorted_dev(), denom, lam_buf(psi, b + 1, k));
+    c->release(r.L);
+    set_site(psi, b, nb);
+    set_site(psi, b + 1, r.R);
+    psi->chi[b + 1] = k;
+    if (specs) fill_spec(r.info, &specs[g]);
+  }
+  psi->llim = -1;
+  psi->rlim = 1;
+  TEVO_CATCH
+}
+
+/* <O_o> on site j of a B-form state: Tr(T^+ O T), T = diag(lam_j) B_j */
+extern "C" int tevo_bform_expect_site(tevo_mps* psi, int j, int nops, const tevo_complex* ops, tevo_complex* out) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && ops && out && nops >= 1 && 2 * nops <= tevo_ctx::NSCAL, "tevo_bform_expect_site: bad argument");
+  require(psi->bform, "tevo_bform_expect_site: state is not in B-form");
+  require(j >= 0 && j < psi->N, "tevo_bform_expect_site: site out of range");
+  tevo_ctx* c = psi->ctx;
+  const int d = psi->d;
+  cplx* dops = (cplx*)c->small(sizeof(cplx) * d * d * nops);
+  upload_small(c, dops, ops, sizeof(cplx) * d * d * nops);
+  expect1(c->stream, psi->site[j].p, psi->chi[j], d, psi->chi[j + 1], psi->lam[j], nops, dops, c->d_scal);
+  download_scalars(c, c->d_scal, 2 * nops, (double*)out);
+  TEVO_CATCH
+}
+
+/* Schmidt values on the bond left of site j (host copies) */
+extern "C" int tevo_mps_get_lambda(tevo_mps* psi, int j, double* host, int cap, int* n_out) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && psi->bform && j >= 0 && j <= psi->N, "tevo_mps_get_lambda: bad argument or not in B-form");
+  const int n = psi->chi[j];
+  if (n_out) *n_out = n;
+  if (host) {
+    require(cap >= n, "tevo_mps_get_lambda: buffer too small");
+    TEVO_CUDA_CHECK(cudaMemcpyAsync(host, psi->lam[j], sizeof(double) * n, cudaMemcpyDeviceToHost, psi->ctx->stream));
+    TEVO_CUDA_CHECK(cudaStreamSynchronize(psi->ctx->stream));
+  }
+  TEVO_CATCH
+}
+
+extern "C" int tevo_mps_set_lambda(tevo_mps* psi, int j, int n, const double* host) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && host && j >= 0 && j <= psi->N && n >= 1, "tevo_mps_set_lambda: bad argument");
+  double* p = lam_buf(psi, j, n);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(p, host, sizeof(double) * n, cudaMemcpyHostToDevice, psi->ctx->stream));
+  TEVO_CUDA_CHECK(cudaStreamSynchronize(psi->ctx->stream));
+  TEVO_CATCH
+}
+
+/* declare a state to be in B-form (all Schmidt vectors set by the caller, e.g. a segment received from a neighbour) */
+extern "C" int tevo_mps_mark_bform(tevo_mps* psi, int on) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi, "null");
+  if (on) {
+    require(!psi->lam.empty(), "tevo_mps_mark_bform: no Schmidt values set");
+    for (int j = 0; j <= psi->N; ++j) require(psi->lam[j] != nullptr, "tevo_mps_mark_bform: missing Schmidt values");
+  }
+  psi->bform = (on != 0);
+  TEVO_CATCH
+}
+
+/* raw device views for peer-to-peer exchange of boundary data (NCCL send/recv from the host layer) */
+extern "C" int tevo_mps_site_devptr(tevo_mps* psi, int j, void** ptr, int* chil, int* chir) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && ptr && j >= 0 && j < psi->N, "tevo_mps_site_devptr: bad argument");
+  *ptr = (void*)psi->site[j].p;
+  if (chil) *chil = psi->chi[j];
+  if (chir) *chir = psi->chi[j + 1];
+  TEVO_CATCH
+}
+
+extern "C" int tevo_mps_lambda_devptr(tevo_mps* psi, int j, void** ptr, int* n) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && ptr && j >= 0 && j <= psi->N && !psi->lam.empty() && psi->lam[j], "tevo_mps_lambda_devptr: bad argument");
+  *ptr = (void*)psi->lam[j];
+  if (n) *n = psi->chi[j];
+  TEVO_CATCH
+}
+
+/* replace site j by a copy of a device buffer (column-major (l,s,r)); lam != NULL also sets lam[j] (n = chil) */
+extern "C" int tevo_mps_set_site_from_device(tevo_mps* psi, int j, int chil, int chir, const void* dev_site) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && dev_site && j >= 0 && j < psi->N && chil >= 1 && chir >= 1, "tevo_mps_set_site_from_device: bad argument");
+  tevo_ctx* c = psi->ctx;
+  const size_t ne = (size_t)chil * psi->d * chir;
+  DevBuf nb = c->alloc(ne);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(nb.p, dev_site, ne * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+  set_site(psi, j, nb);
+  psi->chi[j] = chil;
+  psi->chi[j + 1] = chir;
+  TEVO_CATCH
+}
+
+extern "C" int tevo_mps_set_lambda_from_device(tevo_mps* psi, int j, int n, const void* dev_lam) {
+  TEVO_TRY(psi ? psi->ctx : nullptr)
+  require(psi && dev_lam && j >= 0 && j <= psi->N && n >= 1, "tevo_mps_set_lambda_from_device: bad argument");
+  double* p = lam_buf(psi, j, n);
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(p, dev_lam, sizeof(double) * n, cudaMemcpyDeviceToDevice, psi->ctx->stream));
+  TEVO_CATCH
 }

@@ -159,6 +159,30 @@ class MPS:
     def normalize_site(self, j: int):
         check(load().tevo_mps_normalize_site(self.h, j), self.ctx.h)
 
+    # ---- layer-parallel (B-form) mode ----
+    def to_bform(self):
+        """Canonical form B_j + Schmidt values on every bond (input of the layer-parallel / sharded TEBD mode)."""
+        check(load().tevo_mps_to_bform(self.h), self.ctx.h)
+        return self
+
+    def schmidt_values(self, j: int) -> np.ndarray:
+        """Schmidt values on the bond left of site j (B-form only)."""
+        n = C.c_int()
+        check(load().tevo_mps_get_lambda(self.h, j, None, 0, C.byref(n)), self.ctx.h)
+        out = np.zeros(n.value)
+        check(load().tevo_mps_get_lambda(self.h, j, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, None),
+              self.ctx.h)
+        return out
+
+    def bform_expect(self, ops: Sequence, j: int) -> np.ndarray:
+        mats = np.ascontiguousarray(np.stack([op(o) for o in ops]).astype(np.complex128))
+        out = np.zeros(len(ops), dtype=np.complex128)
+        check(load().tevo_bform_expect_site(self.h, j, len(ops), _addr(mats), _addr(out)), self.ctx.h)
+        return out
+
+    def bform_expect_all(self, o) -> np.ndarray:
+        return np.array([self.bform_expect([o], j)[0].real for j in range(self.N)])
+
     # ---- observables ----
     def measure_bond(self, b: int, ops: Sequence) -> np.ndarray:
         """<O> on sites b, b+1 from theta = psi[b]*psi[b+1] (src/callback.jl:65-73).  Returns (nops, 2) complex."""

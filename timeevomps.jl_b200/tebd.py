@@ -202,3 +202,44 @@ def tebd(psi: MPS, H, dt, tf, alg: Optional[TEBDalg] = None, *, callback: Option
         if cb.checkdone(psi):
             break
     return psi
+
+
+# ------------------------------------------------------------------------------------------------------------
+# layer-parallel mode (NOT the reference's sequential algorithm; the multi-GPU building block)
+# ------------------------------------------------------------------------------------------------------------
+def apply_gates_parallel(psi: MPS, Gs: Sequence[BondGate], **kw):
+    """All gates of one even/odd layer at once on a B-form state (psi.to_bform()); returns the Spectrum of each."""
+    Gs = list(Gs)
+    if not Gs:
+        return []
+    n = len(Gs)
+    bonds = (C.c_int * n)(*[g.b for g in Gs])
+    G = np.ascontiguousarray(np.stack([g.G for g in Gs]).astype(np.complex128))
+    tr = _trunc_from(kw)
+    specs = (tevo_spec * n)()
+    check(load().tevo_apply_layer_bform(psi.h, n, bonds, G.ctypes.data, C.byref(tr), 1 if kw.get("normalize", True) else 0,
+                                        specs, None, 0), psi.ctx.h)
+    return [Spectrum(specs[g]) for g in range(n)]
+
+
+def tebd_parallel(psi: MPS, H, dt, tf, alg: Optional[TEBDalg] = None, **kw) -> MPS:
+    """The schedule of tebd! (bunched half steps, no callbacks) driving layer-parallel updates of a B-form state."""
+    alg = TEBD2() if alg is None else alg
+    if isinstance(H, BondOperator):
+        H = gates(H)
+    nsteps = _nsteps(tf, dt)
+    Ustart, Us, Uend = time_evo_gates(dt, H, alg)
+    nbunch = nsteps + (1 if (len(Ustart) == 0 and len(Uend) == 0) else 0)
+    step = 0
+    while step < nsteps:
+        for U in Ustart:
+            apply_gates_parallel(psi, U, **kw)
+        for _ in range(nbunch - 1):
+            for U in Us:
+                apply_gates_parallel(psi, U, **kw)
+            step += 1
+        for U in Uend:
+            apply_gates_parallel(psi, U, **kw)
+        if len(Uend) > 0:
+            step += 1
+    return psi
