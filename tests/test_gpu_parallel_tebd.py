@@ -58,3 +58,18 @@ def test_parallel_equals_sequential_without_truncation(tevo, oracle):
     ent = [float(-np.sum((l ** 2)[l ** 2 > 1e-13] * np.log((l ** 2)[l ** 2 > 1e-13]))) for l in
            (p.schmidt_values(j) for j in range(1, N))]
     np.testing.assert_allclose(ent, oracle.bond_entropies(o), atol=TOL)
+
+
+def test_device_segment_single_rank_matches_direct(tevo, oracle):
+    """DeviceSegment + ShardedTEBD with world_size 1 (no exchange) == direct layer-parallel TEBD."""
+    from timeevomps_jl_b200.sharded import DeviceSegment, ShardedTEBD
+    N = 8
+    o = oracle.MPS.random(N, 5, seed=9)
+    a = tevo.MPS.from_tensors(o.A, llim=o.llim, rlim=o.rlim).to_bform()
+    b = tevo.MPS.from_tensors(o.A, llim=o.llim, rlim=o.rlim).to_bform()
+    seg = DeviceSegment(a, 0, N, ghost=False)
+    sh = ShardedTEBD(seg, N, None, 0, 1, device="cuda")
+    H = tevo.gates(tevo.tfi_bondop(N, 1.0, 0.5))
+    sh.run(H, 0.05, 2, tevo.time_evo_gates, tevo.TEBD2(), maxdim=6)
+    tevo.tebd_parallel(b, tevo.tfi_bondop(N, 1.0, 0.5), 0.05, 0.1, tevo.TEBD2(), maxdim=6)
+    np.testing.assert_allclose(sh.gather_expect("Sz"), b.bform_expect_all("Sz"), atol=1e-13)

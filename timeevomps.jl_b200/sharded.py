@@ -1,0 +1,221 @@
+"""Chain-segment sharding of layer-parallel TEBD over the GPUs of one node (BASELINE config 5).
+
+Rank r owns the contiguous sites [lo, hi).  It keeps a local B-form chain of its sites plus one ghost site (a copy
+of the right neighbour's first site).  A gate whose two sites straddle the cut (hi-1 | hi) is applied by the left
+owner: before the layer it receives the current B_hi from rank r+1, after the update it sends the new B_hi and the
+new Schmidt values of the cut bond back - one boundary tensor each way per cut and layer, peer to peer
+(torch.distributed send/recv: NCCL over NVLink on the GPUs, gloo in the CPU tests).  No other communication sits on
+the data path; observables are gathered with one small all_gather.
+
+The arithmetic of a segment lives behind the tiny `Segment` interface so that the exchange schedule is tested on
+CPU with a NumPy segment and runs on the device with `DeviceSegment` (libtevo).  Layer-parallel TEBD is not the
+reference's sequential algorithm (see tebd.py / DESIGN.md section 8)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def segment_bounds(N: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous balanced partition of the sites."""
+    return (rank * N) // world, ((rank + 1) * N) // world
+
+
+def owner_of_site(N: int, world: int, j: int) -> int:
+    for r in range(world):
+        lo, hi = segment_bounds(N, world, r)
+        if lo <= j < hi:
+            return r
+    raise ValueError(j)
+
+
+class Segment:
+    """Interface of a rank-local piece of a B-form chain.  Local site i = global site lo + i; local index nloc is the
+    ghost site.  Tensors cross the interface as torch tensors living where the communication backend wants them."""
+
+    def site_tensor(self, i):            # -> (torch tensor of float64 pairs, (chil, d, chir))
+        raise NotImplementedError
+
+    def set_site_tensor(self, i, t, shape):
+        raise NotImplementedError
+
+    def lam_tensor(self, i):             # Schmidt values on the bond left of local site i
+        raise NotImplementedError
+
+    def set_lam_tensor(self, i, t):
+        raise NotImplementedError
+
+    def apply_layer(self, local_gates, **kw):
+        raise NotImplementedError
+
+    def expect_site(self, op, i) -> float:
+        raise NotImplementedError
+
+    def sync(self):
+        pass
+
+
+class ShardedTEBD:
+    def __init__(self, segment: Segment, N: int, dist, rank: int, world: int, device="cpu"):
+        self.seg, self.N, self.dist, self.rank, self.world, self.device = segment, N, dist, rank, world, device
+        self.lo, self.hi = segment_bounds(N, world, rank)
+        self.nloc = self.hi - self.lo
+        self.bytes_sent = 0
+
+    # ---- point-to-point helpers ----
+    def _send(self, t, shape, dst):
+        import torch
+        hdr = torch.tensor(list(shape) + [0] * (3 - len(shape)), dtype=torch.int64, device=self.device)
+        self.dist.send(hdr, dst)
+        self.dist.send(t.contiguous(), dst)
+        self.bytes_sent += t.numel() * t.element_size()
+
+    def _recv(self, src, dtype_elems_per_entry=2):
+        import torch
+        hdr = torch.zeros(3, dtype=torch.int64, device=self.device)
+        self.dist.recv(hdr, src)
+        shape = tuple(int(x) for x in hdr.tolist() if int(x) > 0)
+        n = int(np.prod(shape)) * dtype_elems_per_entry
+        t = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.dist.recv(t, src)
+        return t, shape
+
+    # ---- one Trotter layer ----
+    def apply_layer(self, gates: Sequence, **kw):
+        """gates: BondGate-like objects with global bond .b and matrix .G, all on disjoint bonds."""
+        mine = [g for g in gates if self.lo <= g.b < self.hi]
+        right_cut = self.hi - 1          # bond (hi-1 | hi), owned by this rank
+        left_cut = self.lo - 1           # bond (lo-1 | lo), owned by rank-1
+        has_right = self.rank < self.world - 1 and any(g.b == right_cut for g in gates)
+        has_left = self.rank > 0 and any(g.b == left_cut for g in gates)
+        self.seg.sync()
+        # 1. boundary tensors travel left: my first site goes to the rank that updates the cut bond
+        if has_left:
+            t, shape = self.seg.site_tensor(0)
+            self._send(t, shape, self.rank - 1)
+        if has_right:
+            t, shape = self._recv(self.rank + 1)
+            self.seg.set_site_tensor(self.nloc, t, shape)
+        # 2. local updates (all independent)
+        out = self.seg.apply_layer([(g.b - self.lo, g.G) for g in mine], **kw)
+        self.seg.sync()
+        # 3. updated boundary tensor and cut-bond Schmidt values travel back right
+        if has_right:
+            t, shape = self.seg.site_tensor(self.nloc)
+            self._send(t, shape, self.rank + 1)
+            lt = self.seg.lam_tensor(self.nloc)
+            self._send(lt, (lt.numel(),), self.rank + 1)
+        if has_left:
+            t, shape = self._recv(self.rank - 1)
+            self.seg.set_site_tensor(0, t, shape)
+            lt, lshape = self._recv(self.rank - 1, dtype_elems_per_entry=1)
+            self.seg.set_lam_tensor(0, lt)
+        return out
+
+    def run(self, H_gates, dt, nsteps: int, time_evo_gates, alg, **kw):
+        """The schedule of tebd! (bunched half steps, no callbacks) over the sharded chain."""
+        Ustart, Us, Uend = time_evo_gates(dt, H_gates, alg)
+        for U in Ustart:
+            self.apply_layer(U, **kw)
+        for _ in range(nsteps - 1 if len(Uend) else nsteps):
+            for U in Us:
+                self.apply_layer(U, **kw)
+        for U in Uend:
+            self.apply_layer(U, **kw)
+
+    def gather_expect(self, op) -> np.ndarray:
+        """Per-site expectation values of the whole chain on every rank (one all_gather of N doubles)."""
+        import torch
+        local = np.zeros(self.N)
+        for i in range(self.nloc):
+            local[self.lo + i] = self.seg.expect_site(op, i)
+        t = torch.tensor(local, dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+
+class _DevView:
+    """__cuda_array_interface__ wrapper so torch can view library-owned device memory (no copy)."""
+
+    def __init__(self, ptr: int, ndoubles: int):
+        self.__cuda_array_interface__ = {"shape": (ndoubles,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+class DeviceSegment(Segment):
+    """A rank-local B-form chain held by libtevo (sites lo..hi-1 plus the ghost site)."""
+
+    def __init__(self, global_bform, lo: int, hi: int, ghost: bool):
+        """Copies the segment out of a full B-form chain that lives on this rank's GPU."""
+        from . import _lib
+        from .mps import MPS
+        self._lib = _lib
+        lib = _lib.load()
+        g = global_bform
+        self.ctx, self.d = g.ctx, g.d
+        self.nloc = hi - lo
+        nl = self.nloc + 1                  # always keep the ghost slot (unused on the last rank)
+        self.psi = MPS(max(nl, 2), g.d, g.ctx)
+        for i in range(nl):
+            j = lo + i
+            if j < g.N and (i < self.nloc or ghost):
+                ptr, l, r = C.c_void_p(), C.c_int(), C.c_int()
+                _lib.check(lib.tevo_mps_site_devptr(g.h, j, C.byref(ptr), C.byref(l), C.byref(r)), g.ctx.h)
+                _lib.check(lib.tevo_mps_set_site_from_device(self.psi.h, i, l.value, r.value, ptr), g.ctx.h)
+            else:
+                break
+        for i in range(max(nl, 2) + 1):
+            j = lo + i
+            if j <= g.N and i <= self.nloc + (1 if ghost else 0):
+                ptr, n = C.c_void_p(), C.c_int()
+                _lib.check(lib.tevo_mps_lambda_devptr(g.h, j, C.byref(ptr), C.byref(n)), g.ctx.h)
+                _lib.check(lib.tevo_mps_set_lambda_from_device(self.psi.h, i, n.value, ptr), g.ctx.h)
+            else:
+                one = np.ones(1)
+                _lib.check(lib.tevo_mps_set_lambda(self.psi.h, i, 1, one.ctypes.data_as(C.POINTER(C.c_double))),
+                           g.ctx.h)
+        _lib.check(lib.tevo_mps_mark_bform(self.psi.h, 1), g.ctx.h)
+        self.ctx.synchronize()
+
+    def sync(self):
+        import torch
+        self.ctx.synchronize()
+        torch.cuda.synchronize()
+
+    def site_tensor(self, i):
+        import torch
+        lib = self._lib.load()
+        ptr, l, r = C.c_void_p(), C.c_int(), C.c_int()
+        self._lib.check(lib.tevo_mps_site_devptr(self.psi.h, i, C.byref(ptr), C.byref(l), C.byref(r)), self.ctx.h)
+        n = l.value * self.d * r.value * 2
+        return torch.as_tensor(_DevView(ptr.value, n), device="cuda"), (l.value, self.d, r.value)
+
+    def set_site_tensor(self, i, t, shape):
+        import torch
+        torch.cuda.synchronize()
+        self._lib.check(self._lib.load().tevo_mps_set_site_from_device(self.psi.h, i, shape[0], shape[2],
+                                                                       C.c_void_p(t.data_ptr())), self.ctx.h)
+        self.ctx.synchronize()
+
+    def lam_tensor(self, i):
+        import torch
+        ptr, n = C.c_void_p(), C.c_int()
+        self._lib.check(self._lib.load().tevo_mps_lambda_devptr(self.psi.h, i, C.byref(ptr), C.byref(n)), self.ctx.h)
+        return torch.as_tensor(_DevView(ptr.value, n.value), device="cuda")
+
+    def set_lam_tensor(self, i, t):
+        import torch
+        torch.cuda.synchronize()
+        self._lib.check(self._lib.load().tevo_mps_set_lambda_from_device(self.psi.h, i, t.numel(),
+                                                                         C.c_void_p(t.data_ptr())), self.ctx.h)
+        self.ctx.synchronize()
+
+    def apply_layer(self, local_gates, **kw):
+        from .bondop import BondGate
+        from .tebd import apply_gates_parallel
+        return apply_gates_parallel(self.psi, [BondGate(G, b) for (b, G) in local_gates], **kw)
+
+    def expect_site(self, op, i) -> float:
+        return float(self.psi.bform_expect([op], i)[0].real)
