@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--cpu-sample-gates", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "sequential", "parallel"],
+                    help="sequential: the reference's algorithm (centre moves between gates; default at 1 GPU); "
+                         "parallel: layer-parallel (Hastings) TEBD, chain-segment sharded over the ranks with NCCL "
+                         "boundary exchange (default at >1 GPU, strong scaling of one N-site chain)")
     ap.add_argument("--workload", default="tebd", choices=["tebd", "tdvp"],
                     help="tebd: the headline TEBD4 step (default); tdvp: two-site TDVP step (BASELINE config 4 shape)")
     return ap.parse_args()
@@ -187,6 +191,141 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_sharded(args):
+    """TEBD4 steps/s of ONE N-site chain sharded by contiguous segments over the ranks (BASELINE config 5):
+    layer-parallel (Hastings, B-form) updates, one boundary tensor exchanged each way per cut bond and layer over
+    NCCL P2P.  Strong scaling: the chain is fixed, the ranks split it.  Not the reference's sequential algorithm:
+    identical without truncation, O(discarded weight) apart with it."""
+    import torch
+    import tevo_b200 as t
+    from timeevomps_jl_b200 import replicas
+    from timeevomps_jl_b200.sharded import DeviceSegment, ShardedTEBD, segment_bounds
+    rank, world, local = replicas.world()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = t.default_ctx()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    N, chi = args.nsites, args.chi
+    glob = t.MPS.random(N, chi, seed=0).to_bform()      # same state on every rank; each keeps its segment
+    lo, hi = segment_bounds(N, world, rank)
+    seg = DeviceSegment(glob, lo, hi, ghost=(rank < world - 1))
+    del glob
+    sh = ShardedTEBD(seg, N, dist, rank, world, device="cuda")
+    Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
+    kw = dict(maxdim=chi, mindim=chi)
+
+    def step():
+        for U in Us:
+            sh.apply_layer(U, **kw)
+
+    def barrier():
+        seg.sync()
+        if dist is not None:
+            dist.barrier()
+
+    for U in Ustart:
+        sh.apply_layer(U, **kw)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t.profile_enable(True)
+    t.profile_read(reset=True)
+    n0 = ctx.launch_count()
+    b0 = sh.bytes_sent
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), 0.0)
+    ms = replicas.max_over_ranks(ms, dist, device="cuda")
+    launches = ctx.launch_count() - n0
+    prof = t.profile_read(reset=True)
+    t.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    # end to end: segment uploaded from pinned host memory, one step, segment downloaded - every step
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        from timeevomps_jl_b200._lib import load as _load, check as _check
+        nl = seg.nloc + (1 if rank < world - 1 else 0)
+        host = [seg.psi.site(i) for i in range(nl)]
+        lams = [seg.psi.schmidt_values(i) for i in range(nl + 1)]
+        pinned = []
+        for a in host:
+            buf = torch.empty(a.size * 2, dtype=torch.float64, pin_memory=True)
+            v = buf.numpy().view(np.complex128).reshape(a.shape, order="F")
+            v[...] = a
+            pinned.append(v)
+        nbytes = sum(a.nbytes for a in pinned) + sum(l.nbytes for l in lams)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for i, a in enumerate(pinned):
+                seg.psi.set_site(i, a)
+            for i, l in enumerate(lams):
+                _check(_load().tevo_mps_set_lambda(seg.psi.h, i, len(l), l.ctypes.data_as(C.POINTER(C.c_double))), ctx.h)
+            _check(_load().tevo_mps_mark_bform(seg.psi.h, 1), ctx.h)
+            step()
+            for i in range(nl):
+                out = seg.psi.site(i)
+                if out.shape == pinned[i].shape:
+                    pinned[i][...] = out
+            lams = [seg.psi.schmidt_values(i) for i in range(nl + 1)]
+        barrier()
+        dt_e2e = replicas.max_over_ranks(time.perf_counter() - t0, dist, device="cuda")
+        e2e = {"value": args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(nbytes)}
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    roofline = None
+    if "tridiag_panel" in prof:
+        d = 2
+        dims = [min(d ** min(j, N - j, 40), chi) for j in range(N + 1)]
+        sizes = [d * dims[g.b + 2] for U in Us for g in U if lo <= g.b < hi]    # rho = theta^+ theta is n x n
+        bytes_alg = sum(16.0 * s ** 3 / 3.0 for s in sizes) * args.steps
+        tk = prof["tridiag_panel"]
+        ach = bytes_alg / (tk["ms"] * 1e-3) / 1e9
+        roofline = {"kernel": "tridiag_panel_kernel (rank 0)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches": tk["count"],
+                    "avg_launch_ms": tk["ms"] / tk["count"], "share_of_step": tk["ms"] / total_prof}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic",
+        "config": {"workload": workload_string(args),
+                   "mode": "layer-parallel (Hastings B-form) TEBD: NOT the sequential reference algorithm; equal to it "
+                           "without truncation, O(discarded weight) apart with it",
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   "chain split into %d contiguous segments, one per GPU; boundary tensor + Schmidt "
+                                   "values exchanged per cut bond and layer by NCCL send/recv" % world),
+                   "l2_policy": "inputs larger than L2 (segment of an 8 GiB MPS streamed per step)"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+        "boundary_bytes_sent_per_step_rank0": int((sh.bytes_sent - b0) / max(args.steps, 1)),
+        "wall_ms_per_step": wall * 1e3 / args.steps,
+        "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+    }
+    print(json.dumps(line))
+
+
 def run_tdvp(args):
     """Secondary workload: one two-site TDVP step (right + left sweep, src/tdvp.jl:54-95) of the XXZ chain at the
     BASELINE config-4 shape (default N=64 via --nsites, chi=1024, krylovdim=30, exp_tol=1e-12); one independent
@@ -269,6 +408,10 @@ def main():
         return
     if args.workload == "tdvp":
         run_tdvp(args)
+        return
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.mode == "parallel" or (args.mode == "auto" and world_env > 1):
+        run_sharded(args)
         return
     import torch
     import tevo_b200 as t
