@@ -278,10 +278,10 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
     conj_transpose(st, n, k1, V, n, R1.p, k1, true);
     colnorm2(st, L1.p, m, m, k1, lam2);
   }
-  // discarded weight: when it is a sizeable fraction of the total (stage-1 estimate >= 1e-3 |theta|^2) the difference
-  // |theta|^2 - sum(kept) is accurate to ~1e-13 relative; only small discarded weights need the residual GEMM
+  // discarded weight: when it is a sizeable fraction of the total (stage-1 estimate >= 1e-5 |theta|^2) the difference
+  // |theta|^2 - sum(kept) is accurate to ~1e-11 relative; only small discarded weights need the residual GEMM
   const bool by_difference = (k1 < nfull) && (res.info.sum_all > 0.0) &&
-                             ((res.info.sum_all - res.info.sum_kept) >= 1e-3 * res.info.sum_all);
+                             ((res.info.sum_all - res.info.sum_kept) >= 1e-5 * res.info.sum_all);
   if (k1 < nfull && !by_difference) {  // accurately known discarded weight = error of the kept state
     ProfScope ps(st, P_RESID);
     cplx* resid = ws(2, (size_t)m * n);
