@@ -537,8 +537,17 @@ def main():
         bytes_alg = sum(16.0 * s ** 3 / 3.0 for s in sizes) * args.steps
         tk = prof["tridiag_panel"]
         ach = bytes_alg / (tk["ms"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_panel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"kernel": "tridiag_panel_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_alg / max(tk["count"], 1),
+                    "note": "latency-bound panel kernel: the trailing matrix is L2-resident within a launch, so DRAM "
+                            "traffic (ncu, profiles/r01_panel_traffic.json) is ~1 matrix per launch although 64 "
+                            "matrix-vector products read it algorithmically",
                     "launches": tk["count"], "avg_launch_ms": tk["ms"] / tk["count"],
                     "share_of_step": tk["ms"] / total_prof}
     flops_step = algorithmic_flops_per_gate(chi) * gates_per_step(N)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <string>
 
 namespace tevo {
@@ -42,7 +43,7 @@ struct Status {
     }                                                                                          \
   } while (0)
 
-extern long long g_launches;  // kernels launched by the library (all contexts)
+extern std::atomic<long long> g_launches;  // kernels launched by the library (all contexts)
 #define TEVO_LAUNCHED()                 \
   do {                                  \
     ++tevo::g_launches;                 \

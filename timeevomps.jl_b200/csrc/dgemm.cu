@@ -3,6 +3,8 @@
 // where K_g (the number of non-deflated eigenvalues) lives in device memory - the grid is sized for the worst
 // case and surplus CTAs exit.  Column-major, non-transposed, common leading dimension.
 // CTA tile 128x128, 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA blocks (64 fp64 accumulators/thread).
+#include <mutex>
+
 #include "common.cuh"
 #include "stedc.h"
 
@@ -116,11 +118,10 @@ void dgemm_merge(cudaStream_t st, const MergeDesc* descs_dev, const int* K_dev, 
                  const double* B, double* C, long ld) {
   if (nmerge <= 0) return;
   const size_t smem = (size_t)STAGES * (BK * (BM + APAD) + BN * (BK + BPAD)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  });
   dim3 grid((maxN + BM - 1) / BM, (maxN + BN - 1) / BN, nmerge);
   dgemm_merge_kernel<<<grid, NT, smem, st>>>(descs_dev, K_dev, A, B, C, ld);
   TEVO_LAUNCHED();

@@ -1,3 +1,4 @@
+#include <mutex>
 // Hermitian eigensolver on the device: blocked Householder tridiagonalisation (persistent cooperative panel kernel +
 // DMMA rank-2k trailing updates), tridiagonal divide & conquer (stedc.cu) and compact-WY back-transformation.
 // It is the core of the truncated split (replacebond!, src/bondgate.jl:51, src/tdvp.jl:64): the density matrix
@@ -526,13 +527,12 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   n_ = n;
   A_ = A;
   lda_ = lda;
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * sizeof(cplx) * TRB * TRB)));
-    configured = true;
-  }
+  });
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
   double* acc_norm = acc_;
   double* acc_yv = acc_ + PW;
@@ -550,7 +550,8 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     pa.bar = reinterpret_cast<unsigned*>(acc_ + PW + 2 * PW + 4 * PW * PW);
     pa.d = d_; pa.e = e_; pa.taus = taus_;
     const int nstrips = (n - p0 + RS - 1) / RS;
-    const int grid = std::max(1, std::min(num_sms_, nstrips));
+    const int cap = (max_ctas_ > 0) ? std::min(max_ctas_, num_sms_) : num_sms_;
+    const int grid = std::max(1, std::min(cap, nstrips));
     void* args[] = {&pa};
     const size_t smem = (size_t)(n - p0) * sizeof(cplx);
     {

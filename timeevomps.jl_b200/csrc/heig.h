@@ -13,6 +13,8 @@ class Heig {
   // Afterwards evals() (ascending, device) is valid and vectors() can be called.  No host synchronisation.
   void factor(cudaStream_t st, int n, cplx* A, long lda);
   const double* evals() const { return evals_; }
+  // cap on the CTAs of the panel kernel (two lanes share the SMs in the layer-parallel mode); 0 = all SMs
+  void set_max_ctas(int n) { max_ctas_ = n; }
   // U(:, i) = eigenvector of column perm[i] (indices into the ascending order), i < k.  U is n x k, ld = ldu.
   void vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ldu);
 
@@ -20,6 +22,7 @@ class Heig {
   void ensure(int n);
   Stedc stedc_;
   int num_sms_ = 148;
+  int max_ctas_ = 0;
   int cap_ = 0, n_ = 0;
   cplx* A_ = nullptr;
   long lda_ = 0;

@@ -1,5 +1,7 @@
 // HBM-bound helper kernels of the two-site update: gate application, gauge permutes/transposes, column
 // gathers with scaling, norms, local expectation values and the on-device truncate! logic.
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -404,11 +406,10 @@ void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, con
   while (npow2 < k1) npow2 <<= 1;
   if (npow2 > 8192) throw TevoError(1, "refine_truncate: more than 8192 singular values not supported");
   size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(refine_truncate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
-    configured = true;
-  }
+  });
   int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;
   refine_truncate_kernel<<<1, threads, smem, st>>>(lam2, k1, nfull, sum_all_dev, resid2_dev, resid_by_difference ? 1 : 0, tp,
                                                    sorted, perm, info, npow2);
@@ -440,11 +441,10 @@ void sort_truncate(cudaStream_t st, const double* lam, int nc, int nfull, const 
   while (npow2 < nc) npow2 <<= 1;
   if (npow2 > 8192) throw TevoError(1, "sort_truncate: more than 8192 singular values not supported");
   size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(sort_truncate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
-    configured = true;
-  }
+  });
   int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;
   sort_truncate_kernel<<<1, threads, smem, st>>>(lam, nc, nfull, tp, sorted, perm, info, npow2);
   TEVO_LAUNCHED();

@@ -5,6 +5,7 @@
 namespace tevo {
 
 Prof g_prof;
+thread_local bool tl_prof_thread = true;
 
 static const char* kNames[P_COUNT] = {"theta_gemm", "gate_apply", "rho_gemm",  "tridiag_panel", "tridiag_her2k", "tridiag_wy",
                                       "stedc",      "backtransform", "split_gemm", "residual",    "truncate",      "hop_gemm",

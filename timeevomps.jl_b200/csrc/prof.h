@@ -46,13 +46,14 @@ struct Prof {
   std::string json(bool reset);
 };
 extern Prof g_prof;
+extern thread_local bool tl_prof_thread;  // only the main lane's host thread records
 
 struct ProfScope {
   int id;
   cudaStream_t st;
   cudaEvent_t a = nullptr;
   ProfScope(cudaStream_t s, int i) : id(i), st(s) {
-    if (g_prof.on) {
+    if (g_prof.on && tl_prof_thread) {
       a = g_prof.get();
       cudaEventRecord(a, st);
     }

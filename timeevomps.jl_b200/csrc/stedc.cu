@@ -1,3 +1,4 @@
+#include <mutex>
 // Device-resident divide & conquer for the real symmetric tridiagonal eigenproblem (see stedc.h).
 // Tree: leaves of <= 32 rows solved by one warp each (implicit QL), then log2(n/32) levels of Cuppen merges; all
 // merges of one level run batched in the same launches, data-dependent sizes (deflation counts) stay on the device.
@@ -535,14 +536,13 @@ void Stedc::run(cudaStream_t st, int n, const double* d, const double* e, double
   ensure(n);
   Plan& plan = plan_for(n);
   const long ld = n;
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(merge_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(zhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    configured = true;
-  }
+  });
   if (n > 4096) throw TevoError(1, "stedc: n > 4096 not supported");
   double* D = lam_;  // working eigenvalues (scaled)
   TEVO_CUDA_CHECK(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)n * n, st));

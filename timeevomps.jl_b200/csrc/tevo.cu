@@ -4,7 +4,9 @@
 #include <cmath>
 #include <complex>
 #include <cstring>
+#include <exception>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "../../include/tevo.h"
@@ -33,6 +35,8 @@ struct tevo_ctx {
   double* h_scal = nullptr;  // pinned mirror
   static constexpr int NSCAL = 1024;
   DevBuf ones;  // 1x1x1 identity environment
+  std::vector<tevo_ctx*> aux;  // extra lanes (own stream / workspaces) for the layer-parallel mode, created lazily
+  bool is_aux = false;
 
   cplx* get_ws(int slot, size_t nelem) {
     DevBuf& b = ws[slot];
@@ -343,6 +347,8 @@ extern "C" int tevo_ctx_create(int device, tevo_ctx** out) {
 
 extern "C" int tevo_ctx_destroy(tevo_ctx* ctx) {
   if (!ctx) return TEVO_OK;
+  for (auto* a : ctx->aux) tevo_ctx_destroy(a);
+  ctx->aux.clear();
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& b : ctx->pool) cudaFree(b.p);
@@ -1403,7 +1409,45 @@ extern "C" int tevo_mps_to_bform(tevo_mps* psi) {
   TEVO_CATCH
 }
 
-/* Hastings' inverse-free update of every gate of one layer; the gates are independent (any order). */
+// one Hastings update of bond b, issued on lane context c (its stream, workspaces, split and buffer pool)
+static void bform_gate(tevo_mps* psi, tevo_ctx* c, int b, const cplx* dG_gate, const TruncParams& tp, bool normalize,
+                       tevo_spec* spec, double* eigs, int eigs_cap) {
+  require(b >= 0 && b < psi->N - 1, "tevo_apply_layer_bform: bond out of range");
+  const int d = psi->d;
+  const int chil = psi->chi[b], m = chil * d, kk = psi->chi[b + 1], n = d * psi->chi[b + 2];
+  cplx* C = c->get_ws(WS_THETA, (size_t)m * n);
+  {
+    ProfScope ps(c->stream, P_THETA);
+    zgemm(c->stream, OP_N, OP_N, m, n, kk, ONE, psi->site[b].p, m, psi->site[b + 1].p, kk, ZERO, C, m);
+  }
+  gate_apply(c->stream, C, chil, d, psi->chi[b + 2], dG_gate);
+  cplx* th = c->get_ws(WS_T1, (size_t)m * n);
+  scale_rows(c->stream, m, n, chil, psi->lam[b], C, th);
+  SplitResult r = c->split.run(c->stream, th, m, n, /*left=*/false, tp, false, eigs, eigs_cap,
+                               [&](size_t ne) { return c->alloc(ne); });
+  const int k = r.k;
+  DevBuf nb = c->alloc((size_t)m * k);
+  {
+    ProfScope ps(c->stream, P_SPLIT_GEMM);
+    zgemm(c->stream, OP_N, OP_C, m, k, n, ONE, C, m, r.R.p, k, ZERO, nb.p, m);  // B'_b = C V
+  }
+  const double* denom = normalize ? &c->split.info_dev()->sum_kept : nullptr;
+  if (normalize) zscal_rsqrt(c->stream, (long)m * k, denom, nb.p);
+  sqrt_scaled(c->stream, k, c->split.sorted_dev(), denom, lam_buf(psi, b + 1, k));
+  c->release(r.L);
+  c->release(psi->site[b]);
+  psi->site[b] = nb;
+  c->release(psi->site[b + 1]);
+  psi->site[b + 1] = r.R;
+  for (auto& x : c->split.take_released()) c->release(x);
+  psi->chi[b + 1] = k;
+  if (spec) fill_spec(r.info, spec);
+}
+
+/* Hastings' inverse-free update of every gate of one layer.  The gates are independent (any order), so two host
+ * threads drive two lanes (streams with their own workspaces) that split the layer between them: the eigensolver's
+ * panel kernel is latency-bound (12 % of the warp slots busy), two of them on half the SMs each overlap well.
+ * TEVO_LANES=1 forces the single-lane path. */
 extern "C" int tevo_apply_layer_bform(tevo_mps* psi, int ngates, const int* bonds, const tevo_complex* Gs,
                                       const tevo_trunc* trunc, int normalize, tevo_spec* specs, double* eigs,
                                       int eigs_stride) {
@@ -1415,34 +1459,64 @@ extern "C" int tevo_apply_layer_bform(tevo_mps* psi, int ngates, const int* bond
   cplx* dG = (cplx*)c->small(sizeof(cplx) * d4 * (size_t)std::max(ngates, 1));
   if (ngates) upload_small(c, dG, Gs, sizeof(cplx) * d4 * (size_t)ngates);
   const TruncParams tp = to_params(trunc);
-  for (int g = 0; g < ngates; ++g) {
-    const int b = bonds[g];
-    require(b >= 0 && b < psi->N - 1, "tevo_apply_layer_bform: bond out of range");
-    const int chil = psi->chi[b], m = chil * d, kk = psi->chi[b + 1], n = d * psi->chi[b + 2];
-    cplx* C = c->get_ws(WS_THETA, (size_t)m * n);
-    {
-      ProfScope ps(c->stream, P_THETA);
-      zgemm(c->stream, OP_N, OP_N, m, n, kk, ONE, psi->site[b].p, m, psi->site[b + 1].p, kk, ZERO, C, m);
+  // all bonds must be distinct and non-adjacent (one even/odd layer): the gates then touch disjoint data
+  bool disjoint = true;
+  for (int g = 0; g < ngates && disjoint; ++g)
+    for (int h = g + 1; h < ngates; ++h)
+      if (std::abs(bonds[g] - bonds[h]) < 2) {
+        disjoint = false;
+        break;
+      }
+  static const int nlanes_cfg = [] {
+    const char* e = getenv("TEVO_LANES");
+    int v = e ? atoi(e) : 3;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+  }();
+  const int nl = std::min(nlanes_cfg, ngates);
+  if (!disjoint || nl < 2) {
+    for (int g = 0; g < ngates; ++g)
+      bform_gate(psi, c, bonds[g], dG + (size_t)g * d4, tp, normalize != 0, specs ? &specs[g] : nullptr,
+                 eigs ? eigs + (size_t)g * eigs_stride : nullptr, eigs ? eigs_stride : 0);
+  } else {
+    while ((int)c->aux.size() < nl - 1) {
+      tevo_ctx* aux = nullptr;
+      int st = tevo_ctx_create(c->device, &aux);
+      if (st != TEVO_OK) throw TevoError(st, std::string("cannot create an extra lane: ") + tevo_last_error(nullptr));
+      aux->is_aux = true;
+      c->aux.push_back(aux);
     }
-    gate_apply(c->stream, C, chil, d, psi->chi[b + 2], dG + (size_t)g * d4);
-    cplx* th = c->get_ws(WS_T1, (size_t)m * n);
-    scale_rows(c->stream, m, n, chil, psi->lam[b], C, th);
-    SplitResult r = c->split.run(c->stream, th, m, n, /*left=*/false, tp, false, eigs ? eigs + (size_t)g * eigs_stride : nullptr,
-                                 eigs ? eigs_stride : 0, [&](size_t ne) { return c->alloc(ne); });
-    const int k = r.k;
-    DevBuf nb = c->alloc((size_t)m * k);
-    {
-      ProfScope ps(c->stream, P_SPLIT_GEMM);
-      zgemm(c->stream, OP_N, OP_C, m, k, n, ONE, C, m, r.R.p, k, ZERO, nb.p, m);  // B'_b = C V
-    }
-    const double* denom = normalize ? &c->split.info_dev()->sum_kept : nullptr;
-    if (normalize) zscal_rsqrt(c->stream, (long)m * k, denom, nb.p);
-    sqrt_scaled(c->stream, k, c->split.sorted_dev(), denom, lam_buf(psi, b + 1, k));
-    c->release(r.L);
-    set_site(psi, b, nb);
-    set_site(psi, b + 1, r.R);
-    psi->chi[b + 1] = k;
-    if (specs) fill_spec(r.info, &specs[g]);
+    std::vector<tevo_ctx*> lanes;
+    lanes.push_back(c);
+    for (int i = 0; i < nl - 1; ++i) lanes.push_back(c->aux[i]);
+    TEVO_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // gates uploaded, previous layer complete
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+    for (auto* l : lanes) l->split.heig().set_max_ctas(std::max(8, nsm / nl));
+    if (psi->lam.empty()) throw TevoError(TEVO_EINTERNAL, "B-form state without Schmidt values");
+    std::vector<std::exception_ptr> err(nl, nullptr);
+    auto work = [&](int lane) {
+      try {
+        TEVO_CUDA_CHECK(cudaSetDevice(c->device));
+        tevo_ctx* lc = lanes[lane];
+        for (int g = lane; g < ngates; g += nl)
+          bform_gate(psi, lc, bonds[g], dG + (size_t)g * d4, tp, normalize != 0, specs ? &specs[g] : nullptr,
+                     eigs ? eigs + (size_t)g * eigs_stride : nullptr, eigs ? eigs_stride : 0);
+        TEVO_CUDA_CHECK(cudaStreamSynchronize(lc->stream));
+      } catch (...) {
+        err[lane] = std::current_exception();
+      }
+    };
+    std::vector<std::thread> ths;
+    for (int i = 1; i < nl; ++i)
+      ths.emplace_back([&, i] {
+        tevo::tl_prof_thread = false;
+        work(i);
+      });
+    work(0);
+    for (auto& th : ths) th.join();
+    for (auto* l : lanes) l->split.heig().set_max_ctas(0);
+    for (int i = 0; i < nl; ++i)
+      if (err[i]) std::rethrow_exception(err[i]);
   }
   psi->llim = -1;
   psi->rlim = 1;

@@ -11,6 +11,8 @@
 // an m8n8k4 fragment, so no planar repack is required.  A complex MAC is 4 real DMMAs:
 //   Cre += Are*Bre ; Cre += (-Aim)*Bim ; Cim += Are*Bim ; Cim += Aim*Bre .
 // CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread).
+#include <mutex>
+
 #include "common.cuh"
 #include "zgemm.h"
 
@@ -188,12 +190,11 @@ void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, lon
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
-  static bool configured = false;
-  if (!configured) {
+  static std::once_flag once;
+  std::call_once(once, [&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
-    configured = true;
-  }
+  });
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
   zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc,
                                                           splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC);
@@ -236,7 +237,7 @@ void launch_split(cudaStream_t st, int M, int N, int K, const cplx* A, long lda,
 }  // namespace
 
 long g_zgemm_launches = 0;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
            long ldb, cplx beta, cplx* C, long ldc) {
