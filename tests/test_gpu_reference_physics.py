@@ -132,10 +132,20 @@ def test_tdvp_free_fermions(tevo, oracle):
         assert np.all(np.abs(ns[i] - ns_exact[i + 1]) < 5e-5)             # test_tdvp.jl:96-117 (N=12, tf=0.5)
 
 
-def test_tdvp_nonhermitian_is_rejected_loudly(tevo):
-    psi = tevo.MPS.product([0] * 6)
-    with pytest.raises(tevo.TevoError):
-        tevo.tdvp(psi, tevo.tfi_mpo(1.0, 0.5, 6), 0.1, 0.1, hermitian=False)
+def test_tdvp_arnoldi_branch_matches_lanczos_and_oracle(tevo, oracle):
+    """hermitian=false (KrylovKit Arnoldi, src/tdvp.jl:25-27,40): same evolution as the Lanczos branch for a
+    Hermitian H, and parity with the oracle's Arnoldi restatement."""
+    N = 8
+    o0 = oracle.MPS.random(N, 3, seed=4)
+    a = tevo.MPS.from_tensors(o0.A, llim=-1, rlim=1)
+    b = tevo.MPS.from_tensors(o0.A, llim=-1, rlim=1)
+    H = tevo.xxz_mpo(N, 0.7, 0.2)
+    tevo.tdvp(a, H, 0.05, 0.1, maxdim=8, exp_tol=1e-12, hermitian=True)
+    tevo.tdvp(b, H, 0.05, 0.1, maxdim=8, exp_tol=1e-12, hermitian=False)
+    assert a.bond_dims() == b.bond_dims()
+    assert abs(abs(tevo.inner(a, b)) - 1.0) < 1e-10
+    oracle.tdvp(o0, oracle.xxz_mpo(N, 0.7, 0.2), 0.05, 0.1, maxdim=8, exp_tol=1e-12, hermitian=False)
+    np.testing.assert_allclose(b.copy().expect_all("Sz"), oracle.expect_all(o0, "Sz"), atol=1e-10)
 
 
 def test_callbacks_during_evolution(tevo, oracle):

@@ -1100,6 +1100,54 @@ static void tridiag_eigh(int k, const std::vector<double>& alpha, const std::vec
   }
 }
 
+// first column of exp(x * H) for a small dense k x k complex matrix (row-major): scaling and squaring with a Taylor
+// series; used by the Arnoldi (hermitian=false) branch of exponentiate
+static std::vector<std::complex<double>> small_expm_col0(int k, const std::vector<std::complex<double>>& H,
+                                                         std::complex<double> x) {
+  typedef std::complex<double> cd;
+  std::vector<cd> A((size_t)k * k);
+  double nrm = 0.0;
+  for (int i = 0; i < k; ++i) {
+    double row = 0.0;
+    for (int j = 0; j < k; ++j) {
+      A[(size_t)i * k + j] = x * H[(size_t)i * k + j];
+      row += std::abs(A[(size_t)i * k + j]);
+    }
+    nrm = std::max(nrm, row);
+  }
+  int s = 0;
+  while (nrm > 0.25 && s < 60) {
+    nrm *= 0.5;
+    ++s;
+  }
+  const double sc = std::ldexp(1.0, -s);
+  for (auto& v : A) v *= sc;
+  std::vector<cd> E((size_t)k * k, cd(0.0)), T((size_t)k * k, cd(0.0)), W((size_t)k * k);
+  for (int i = 0; i < k; ++i) E[(size_t)i * k + i] = T[(size_t)i * k + i] = 1.0;
+  auto matmul = [&](const std::vector<cd>& X, const std::vector<cd>& Y, std::vector<cd>& Z) {
+    for (int i = 0; i < k; ++i)
+      for (int j = 0; j < k; ++j) {
+        cd acc = 0.0;
+        for (int l = 0; l < k; ++l) acc += X[(size_t)i * k + l] * Y[(size_t)l * k + j];
+        Z[(size_t)i * k + j] = acc;
+      }
+  };
+  for (int j = 1; j <= 20; ++j) {
+    matmul(T, A, W);
+    for (size_t i = 0; i < W.size(); ++i) {
+      T[i] = W[i] / (double)j;
+      E[i] += T[i];
+    }
+  }
+  for (int q = 0; q < s; ++q) {
+    matmul(E, E, W);
+    E.swap(W);
+  }
+  std::vector<cd> col(k);
+  for (int i = 0; i < k; ++i) col[i] = E[(size_t)i * k];
+  return col;
+}
+
 struct KrylovParams {
   bool hermitian;
   double tol;
@@ -1110,7 +1158,6 @@ struct KrylovParams {
 static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx* w, const KrylovParams& kp) {
   tevo_ctx* c = h.c;
   tevo_krylov_info info = {0, 0, 0};
-  if (!kp.hermitian) throw TevoError(TEVO_EINVAL, "exponentiate: hermitian=false (Arnoldi) is not implemented yet");
   const long n = h.n;
   const double tau_total = std::abs(t);
   if (tau_total == 0.0) {
@@ -1130,6 +1177,15 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
   double tau_done = 0.0;
   const double eta = kp.tol;
   std::vector<double> alpha(kd), beta(kd), D, U;
+  const bool herm = kp.hermitian;
+  std::vector<std::complex<double>> Hess;  // Arnoldi: (kd+1) x kd upper Hessenberg, row-major with row stride kd
+  if (!herm) Hess.assign((size_t)(kd + 1) * kd, 0.0);
+  auto hess_block = [&](int kk) {
+    std::vector<std::complex<double>> Hk((size_t)kk * kk);
+    for (int i = 0; i < kk; ++i)
+      for (int j = 0; j < kk; ++j) Hk[(size_t)i * kk + j] = Hess[(size_t)i * kd + j];
+    return Hk;
+  };
   while (true) {
     info.numiter += 1;
     // beta0 = |w|
@@ -1146,8 +1202,15 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
     int k = 0;
     bool done_sub = false;
     double nb = 0.0;
+    if (!herm) std::fill(Hess.begin(), Hess.end(), std::complex<double>(0.0));
     auto estimate = [&](int kk, double dt, double nbv) {
       std::complex<double> e1 = 0.0, e2 = 0.0;
+      if (!herm) {
+        const auto Hk = hess_block(kk);
+        e1 = small_expm_col0(kk, Hk, sgn * (dt / 2))[kk - 1];
+        e2 = small_expm_col0(kk, Hk, sgn * dt)[kk - 1];
+        return nbv * (2.0 * std::abs(e1) / 3.0 + std::abs(e2) / 6.0);
+      }
       for (int j = 0; j < kk; ++j) {
         const double ukj = U[(size_t)(kk - 1) * kk + j], u1j = U[j];
         e1 += ukj * std::exp(sgn * (dt / 2) * D[j]) * u1j;
@@ -1168,8 +1231,14 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
       alpha[k] = hs[2 * k] + hs[2 * (kd + 1) + 2 * k];
       nb = std::sqrt(std::max(0.0, hs[4 * (kd + 1)]));
       beta[k] = nb;
+      if (!herm) {
+        for (int i = 0; i <= k; ++i)
+          Hess[(size_t)i * kd + k] = std::complex<double>(hs[2 * i] + hs[2 * (kd + 1) + 2 * i],
+                                                          hs[2 * i + 1] + hs[2 * (kd + 1) + 2 * i + 1]);
+        Hess[(size_t)(k + 1) * kd + k] = nb;
+      }
       k += 1;
-      tridiag_eigh(k, alpha, beta, D, U);
+      if (herm) tridiag_eigh(k, alpha, beta, D, U);
       const double eps = estimate(k, dtau, nb);
       if (eps < eta || (long)k == n) {
         done_sub = true;
@@ -1186,6 +1255,13 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
     }
     // y = U exp(sgn*dtau*D) U^T e1
     std::vector<double> y(2 * k, 0.0);
+    if (!herm) {
+      const auto col = small_expm_col0(k, hess_block(k), sgn * dtau);
+      for (int i = 0; i < k; ++i) {
+        y[2 * i] = col[i].real();
+        y[2 * i + 1] = col[i].imag();
+      }
+    } else
     for (int i = 0; i < k; ++i) {
       std::complex<double> acc = 0.0;
       for (int j = 0; j < k; ++j) acc += U[(size_t)i * k + j] * std::exp(sgn * dtau * D[j]) * U[j];
