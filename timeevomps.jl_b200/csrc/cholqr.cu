@@ -136,7 +136,7 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   TEVO_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(cplx) * (size_t)n * n, st));
   {
     ProfScope ps(st, P_CHOL_GRAM);
-    zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G_, n);
+    zgemm_herm(st, OP_C, OP_N, n, m, ONE, A, m, A, m, ZERO, G_, n, false);  // Cholesky reads the lower part only
   }
   ProfScope* pf = new ProfScope(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
@@ -148,8 +148,8 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
       // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H ; trailing: G(j+nb:, j+nb:) -= panel * panel^H
       zgemm(st, OP_N, OP_C, rest, nb, nb, ONE, G_ + (long)j * n + j + nb, n, X + (long)j * n + j, n, ZERO,
             L + (long)j * n + j + nb, n);
-      zgemm(st, OP_N, OP_C, rest, rest, nb, MONE, L + (long)j * n + j + nb, n, L + (long)j * n + j + nb, n, ONE,
-            G_ + (long)(j + nb) * n + j + nb, n);
+      zgemm_herm(st, OP_N, OP_C, rest, nb, MONE, L + (long)j * n + j + nb, n, L + (long)j * n + j + nb, n, ONE,
+                 G_ + (long)(j + nb) * n + j + nb, n, false);
     }
   }
   delete pf;
@@ -234,7 +234,7 @@ bool CholQR::factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx*
   // GEMMs instead of a second Cholesky factorisation; otherwise the full CholeskyQR pass is repeated.
   {
     ProfScope ps(st, P_CHOL_GRAM);
-    zgemm(st, OP_C, OP_N, n, n, m, ONE, Q1_, m, Q1_, m, ZERO, G_, n);
+    zgemm_herm(st, OP_C, OP_N, n, m, ONE, Q1_, m, Q1_, m, ZERO, G_, n, true);
   }
   unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(d_stats_ + 2 * 127);
   TEVO_CUDA_CHECK(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), st));

@@ -29,12 +29,6 @@ __host__ __device__ inline void cfma(cplx& a, cplx x, cplx y) {
 
 enum Op { OP_N = 0, OP_T = 1, OP_C = 2 };
 
-// error plumbing: every internal function returns cudaError_t-like int; the C ABI maps to TEVO_* codes
-struct Status {
-  int code = 0;
-  std::string msg;
-};
-
 #define TEVO_CUDA_CHECK(expr)                                                                  \
   do {                                                                                         \
     cudaError_t _e = (expr);                                                                   \

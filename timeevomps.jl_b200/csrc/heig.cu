@@ -570,7 +570,7 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H
     ProfScope ps2(st, P_TRI_HER2K);
     if (pw == PW) {
-      zgemm(st, OP_N, OP_C, n - q0, n - q0, 2 * PW, MONE, P_ + q0, n, Q_ + q0, n, ONE, A + (long)q0 * lda + q0, lda);
+      zgemm_herm(st, OP_N, OP_C, n - q0, 2 * PW, MONE, P_ + q0, n, Q_ + q0, n, ONE, A + (long)q0 * lda + q0, lda, true);
     } else {
       zgemm(st, OP_N, OP_C, n - q0, n - q0, pw, MONE, P_ + q0, n, Q_ + q0, n, ONE, A + (long)q0 * lda + q0, lda);
       zgemm(st, OP_N, OP_C, n - q0, n - q0, pw, MONE, P_ + (long)PW * n + q0, n, Q_ + (long)PW * n + q0, n, ONE,

@@ -139,34 +139,6 @@ SplitResult Split::run_jacobi(cudaStream_t st, const cplx* theta, int m, int n, 
 // Discarded weight = |theta - L R|_F^2, i.e. the error of the state actually kept.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
-__global__ void finalize_spec_kernel(int k, int nfull, const double* __restrict__ lam2, const double* __restrict__ scal,
-                                     TruncParams tp, int truncated, TruncInfo* info) {
-  __shared__ double red[2 * 32];
-  double v[2] = {0.0, 0.0};
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const double p = lam2[i];
-    v[0] += p;
-    if (p > 1e-13) v[1] -= p * log(p);
-  }
-  block_sum<2>(v, red);
-  if (threadIdx.x == 0) {
-    const double sum_all = scal[0];
-    info->sum_kept = v[0];
-    info->entropy = v[1];
-    info->sum_all = sum_all;
-    double te = 0.0;
-    if (truncated) {
-      te = scal[2] > 0.0 ? scal[2] : 0.0;
-      if (!tp.use_absolute_cutoff) {
-        double scale = 1.0;
-        if (tp.do_rel_cutoff) scale = (sum_all == 0.0) ? 1.0 : sum_all;
-        te /= scale;
-      }
-    }
-    info->truncerr = te;
-  }
-}
-
 // rows of R (k x n, ld): out[i] = sum_j |R(i,j)|^2
 __global__ void rownorm2_kernel(int k, int n, const cplx* __restrict__ R, long ld, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -243,9 +215,9 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
   {
     ProfScope ps(st, P_RHO);
     if (left)
-      zgemm(st, OP_N, OP_C, m, m, n, ONE, theta, m, theta, m, ZERO, rho, m);
+      zgemm_herm(st, OP_N, OP_C, m, n, ONE, theta, m, theta, m, ZERO, rho, m, true);
     else
-      zgemm(st, OP_C, OP_N, n, n, m, ONE, theta, m, theta, m, ZERO, rho, n);
+      zgemm_herm(st, OP_C, OP_N, n, m, ONE, theta, m, theta, m, ZERO, rho, n, true);
   }
   heig_.factor(st, N, rho, N);
   // stage 1: candidate count k1 from the Gram spectrum, with a safety margin of the size of its rounding noise so
@@ -368,9 +340,9 @@ SplitResult Split::ortho_factor(cudaStream_t st, const cplx* A, int m, int n, bo
   {
     ProfScope ps(st, P_RHO);
     if (left)
-      zgemm(st, OP_C, OP_N, n, n, m, ONE, A, m, A, m, ZERO, G, n);
+      zgemm_herm(st, OP_C, OP_N, n, m, ONE, A, m, A, m, ZERO, G, n, true);
     else
-      zgemm(st, OP_N, OP_C, m, m, n, ONE, A, m, A, m, ZERO, G, m);
+      zgemm_herm(st, OP_N, OP_C, m, n, ONE, A, m, A, m, ZERO, G, m, true);
   }
   heig_.factor(st, k, G, k);
   sort_truncate(st, heig_.evals(), k, k, tp, d_sorted_, d_perm_, d_info_);

@@ -70,7 +70,7 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
-                  long part_stride, int nsplit, long bsA, long bsB, long bsC) {
+                  long part_stride, int nsplit, long bsA, long bsB, long bsC, int lower_only) {
   // blockIdx.z = batch * nsplit + split.  split-K: split s handles k in [s*Kc, min(Kfull, (s+1)*Kc)) and writes its
   // partial product to C + s*part_stride; batched: operands of batch b are offset by b*bsA / b*bsB / b*bsC
   const int zsplit = blockIdx.z % nsplit, zbatch = blockIdx.z / nsplit;
@@ -89,6 +89,7 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   cplx* sB = sA + STAGES * TA::elems;
 
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (lower_only && n0 >= m0 + BM) return;  // Hermitian result: tiles strictly above the diagonal are mirrored later
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
   const int g = lane >> 2, tq = lane & 3;
@@ -186,7 +187,7 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
 template <bool AK, bool BK_>
 void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
             long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0,
-            int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0) {
+            int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0, int lower_only = 0) {
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
@@ -197,7 +198,8 @@ void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, lon
   });
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
   zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc,
-                                                          splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC);
+                                                          splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC,
+                                                          lower_only);
   TEVO_LAUNCHED();
 }
 
@@ -264,6 +266,53 @@ void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const
     launch<false, false>(st, M, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc);
 }
 
+
+// Hermitian-result variant (C = alpha op(A) op(B) + beta C is known to be Hermitian, M == N): only the CTA tiles that
+// touch the lower triangle are computed; mirror != 0 then writes conj(lower) into the strict upper triangle.
+__global__ void mirror_lower_kernel(int n, cplx* __restrict__ C, long ldc) {
+  __shared__ cplx tile[32][33];
+  const int bi = blockIdx.x, bj = blockIdx.y;  // tile (bi, bj) of the lower triangle, bi >= bj
+  if (bi < bj) return;
+  const int r0 = bi * 32, c0 = bj * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + threadIdx.x, c = c0 + j;
+    if (r < n && c < n) tile[j][threadIdx.x] = C[(long)c * ldc + r];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    // element (c0 + threadIdx.x, r0 + j) of the upper triangle = conj(C(r0 + j, c0 + threadIdx.x))
+    const int rr = c0 + threadIdx.x, cc = r0 + j;
+    if (rr < n && cc < n && rr < cc) {
+      const cplx v = tile[threadIdx.x][j];
+      C[(long)cc * ldc + rr] = mk(v.x, -v.y);
+    }
+  }
+}
+
+void zgemm_herm(cudaStream_t st, Op ta, Op tb, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B, long ldb,
+                cplx beta, cplx* C, long ldc, bool mirror) {
+  if (N <= 0) return;
+  if (K <= 0) {
+    zgemm(st, ta, tb, N, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    return;
+  }
+  ++g_zgemm_launches;
+  const bool ak = (ta != OP_N), bk = (tb == OP_N);
+  const int ca = (ta == OP_C), cb = (tb == OP_C);
+  if (ak && bk)
+    launch<true, true>(st, N, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, 1, 0, 0, 0, 1);
+  else if (ak && !bk)
+    launch<true, false>(st, N, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, 1, 0, 0, 0, 1);
+  else if (!ak && bk)
+    launch<false, true>(st, N, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, 1, 0, 0, 0, 1);
+  else
+    launch<false, false>(st, N, N, K, alpha, A, lda, ca, B, ldb, cb, beta, C, ldc, 1, 0, 0, 1, 0, 0, 0, 1);
+  if (mirror && N > 1) {
+    dim3 grid((N + 31) / 32, (N + 31) / 32), block(32, 8);
+    mirror_lower_kernel<<<grid, block, 0, st>>>(N, C, ldc);
+    TEVO_LAUNCHED();
+  }
+}
 
 // Strided-batched variant: `batch` independent products with operand strides bsA / bsB / bsC (elements).
 void zgemm_batched(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, long bsA,

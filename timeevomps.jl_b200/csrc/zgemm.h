@@ -6,6 +6,9 @@ void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const
            long ldb, cplx beta, cplx* C, long ldc);
 void zgemm_splitk(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
                   long ldb, cplx beta, cplx* C, long ldc, cplx** part, size_t* part_cap);
+// C (N x N) Hermitian: lower-triangle tiles only (+ optional mirror of conj(lower) into the strict upper part)
+void zgemm_herm(cudaStream_t st, Op ta, Op tb, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B, long ldb,
+                cplx beta, cplx* C, long ldc, bool mirror);
 void zgemm_batched(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, long bsA,
                    const cplx* B, long ldb, long bsB, cplx beta, cplx* C, long ldc, long bsC, int batch);
 extern long g_zgemm_launches;
