@@ -17,30 +17,36 @@ namespace {
 constexpr int PW = 64;  // panel width
 constexpr int RS = 16;  // rows per strip
 constexpr int NT = 256;
+constexpr int NREP = 8;        // replicas of the panel-dot accumulators (same-address L2 atomics serialise)
+constexpr int PANEL_SMEM = 200 * 1024;  // dynamic shared memory budget of the panel kernel
+constexpr int MAXCTA = 256;    // slots of the per-CTA arrays (flags, partial norms)
 
 struct PanelArgs {
   int n, p0, pw;
+  int smax;  // strips per CTA whose rows of V, W (and y, next column) are kept in shared memory
   cplx* A;
   long lda;
   cplx* P;  // n x 2*PW : [V | W]
   cplx* Q;  // n x 2*PW : [W | V]
   cplx* Y;  // n x PW   : raw y = A22 v
   long ldp;
-  double* acc_norm;  // PW
-  double* acc_yv;    // 2*PW
-  double* acc_cw;    // 2*PW*PW
-  double* acc_cv;    // 2*PW*PW   (kept: V^H v, the strictly upper part of V^H V for the compact-WY T factor)
-  unsigned* bar;     // grid barrier counter (zeroed before the launch)
+  double* pnorm;     // per-CTA partial |x|^2 of the current column (rewritten every column, never zeroed)
+  double* pyv;       // per-CTA partial y^H v (2 doubles per CTA)
+  double* acc_cw;    // NREP x 2*PW*PW : W^H v, accumulated with atomics into replica blockIdx % NREP
+  double* acc_cv;    // NREP x 2*PW*PW : V^H v
+  double* cv_out;    // 2*PW*PW  (kept: V^H v, the strictly upper part of V^H V for the compact-WY T factor)
+  unsigned* arrive;  // grid barrier words (zeroed before the launch), MAXCTA lines each
+  unsigned* release;
   double* d;
   double* e;
   cplx* taus;
 };
 
 #ifdef TEVO_PANEL_TIMING
-__device__ unsigned long long g_panel_cycles[8];
+__device__ unsigned long long g_panel_cycles[16];
 #define PT_MARK(slot)                                                     \
   do {                                                                    \
-    if (blockIdx.x == 0 && threadIdx.x == 0) {                            \
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {                \
       long long _now = clock64();                                         \
       atomicAdd(&g_panel_cycles[slot], (unsigned long long)(_now - _t0)); \
       _t0 = _now;                                                         \
@@ -52,19 +58,67 @@ __device__ unsigned long long g_panel_cycles[8];
 
 __device__ inline cplx ldcg_c(const cplx* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
-// grid-wide barrier for the co-resident (cooperatively launched) panel kernel: one arrival per CTA on a
-// monotonically increasing counter.  Data produced by other CTAs is read with ld.cg afterwards.
-__device__ inline void grid_bar(unsigned* ctr, unsigned target) {
+// grid-wide barrier for the co-resident (cooperatively launched) panel kernel.  Data produced by other CTAs is read
+// with ld.cg afterwards.  Same-address traffic serialises in L2 (atomics ~27 cycles each), so the variants differ in
+// who touches which line:  0 = one atomic counter polled by everybody, 1 = one word per CTA polled by everybody,
+// 2 = gather/release: CTA 0 polls one line per CTA and then writes one release line per CTA.
+#ifndef TEVO_BAR
+#define TEVO_BAR 0
+#endif
+constexpr int FLAG_STRIDE = 32;  // words: one 128-byte line per CTA
+__device__ inline unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ inline void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ inline void grid_bar(unsigned* arrive, unsigned* release, unsigned epoch) {
   __syncthreads();
+#if TEVO_BAR == 0
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
+    atomicAdd(arrive, 1u);
+    const unsigned target = epoch * gridDim.x;
+    while (ld_relaxed_u32(arrive) < target) {
+    }
     __threadfence();
   }
+#elif TEVO_BAR == 1
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_relaxed_u32(arrive + blockIdx.x, epoch);
+    }
+    const int G = gridDim.x;
+    for (;;) {
+      bool ok = true;
+      for (int k = threadIdx.x; k < G; k += 32) ok = ok && (ld_relaxed_u32(arrive + k) >= epoch);
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
+    __threadfence();
+  }
+#else
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 32) {
+      const int G = gridDim.x;
+      for (;;) {
+        bool ok = true;
+        for (int k = 1 + threadIdx.x; k < G; k += 32) ok = ok && (ld_relaxed_u32(arrive + k * FLAG_STRIDE) >= epoch);
+        if (__all_sync(0xffffffffu, ok)) break;
+      }
+      __threadfence();  // acquire for the arrivals, release for the stores below (and for this CTA's own data)
+      for (int k = 1 + threadIdx.x; k < G; k += 32) st_relaxed_u32(release + k * FLAG_STRIDE, epoch);
+    }
+  } else if (threadIdx.x == 0) {
+    __threadfence();
+    st_relaxed_u32(arrive + blockIdx.x * FLAG_STRIDE, epoch);
+    while (ld_relaxed_u32(release + blockIdx.x * FLAG_STRIDE) < epoch) {
+    }
+    __threadfence();
+  }
+#endif
   __syncthreads();
 }
 
@@ -106,9 +160,14 @@ __device__ inline cplx reduce_cl(cplx v, cplx* sred) {
 __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx* sv = reinterpret_cast<cplx*>(smraw);  // v (n - p0 entries max)
+  // resident copies of the own rows: per strip [V: PW x RS | W: PW x RS | y: RS | next column: RS]
+  constexpr int SB = 2 * PW * RS + 2 * RS;
+  cplx* sres = sv + ((a.n - a.p0 + 1) & ~1);
+  const int smax = a.smax;
   __shared__ cplx sred[2 * NT];
   __shared__ cplx pivV[PW], pivW[PW], scw[PW], scv[PW];
   __shared__ cplx s_tau_prev, s_alpha_prev, s_yv, s_ypiv;
+  __shared__ double s_xn2;
   __shared__ double sblk[64];
   const int n = a.n, p0 = a.p0, pw = a.pw;
   const int tid = threadIdx.x, rr = tid % RS, cl = tid / RS;
@@ -118,6 +177,13 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   cplx* Yp = a.Y;
   unsigned epoch = 0;
   cplx tau_cur = mk(0, 0);
+  // own rows of the panel vectors: shared memory for the first smax strips of this CTA, global memory beyond
+  auto ldV = [&](int sidx, int k, int r) -> cplx {
+    return sidx < smax ? sres[sidx * SB + k * RS + (threadIdx.x % RS)] : Vp[(long)k * a.ldp + r];
+  };
+  auto ldW = [&](int sidx, int k, int r) -> cplx {
+    return sidx < smax ? sres[sidx * SB + (PW + k) * RS + (threadIdx.x % RS)] : Wp[(long)k * a.ldp + r];
+  };
 #ifdef TEVO_PANEL_TIMING
   long long _t0 = clock64();
 #endif
@@ -131,17 +197,43 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       const int ip = i - 1;
       for (int k = tid; k < i; k += NT) {
         if (k < ip) {
-          scw[k] = mk(__ldcg(&a.acc_cw[2 * (ip * PW + k)]), __ldcg(&a.acc_cw[2 * (ip * PW + k) + 1]));
-          scv[k] = mk(__ldcg(&a.acc_cv[2 * (ip * PW + k)]), __ldcg(&a.acc_cv[2 * (ip * PW + k) + 1]));
+          cplx w[NREP], v[NREP];
+#pragma unroll
+          for (int q = 0; q < NREP; ++q) {
+            w[q] = ldcg_c(reinterpret_cast<const cplx*>(a.acc_cw) + (long)q * PW * PW + ip * PW + k);
+            v[q] = ldcg_c(reinterpret_cast<const cplx*>(a.acc_cv) + (long)q * PW * PW + ip * PW + k);
+          }
           if (i < pw) pivW[k] = ldcg_c(&Wp[(long)k * a.ldp + c]);
+#pragma unroll
+          for (int q = 1; q < NREP; ++q) {
+            w[0] = cadd(w[0], w[q]);
+            v[0] = cadd(v[0], v[q]);
+          }
+          scw[k] = w[0];
+          scv[k] = v[0];
+          if (blockIdx.x == 0) reinterpret_cast<cplx*>(a.cv_out)[ip * PW + k] = v[0];
         }
         if (i < pw) pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
       }
-      if (tid == NT - 1) {  // a thread of another warp than the one that reduces below
-        s_yv = mk(__ldcg(&a.acc_yv[2 * ip]), __ldcg(&a.acc_yv[2 * ip + 1]));
-        if (i < pw) s_ypiv = ldcg_c(&Yp[(long)ip * a.ldp + c]);
+      if (tid >= NT - 32) {  // another warp than the one that reduces below: y^H v from the per-CTA partials
+        const int lane = tid - (NT - 32);
+        cplx ypiv = mk(0, 0);
+        if (lane == 0 && i < pw) ypiv = ldcg_c(&Yp[(long)ip * a.ldp + c]);  // in flight with the partials below
+        double y0 = 0.0, y1 = 0.0;
+        for (int g = lane; g < (int)gridDim.x; g += 32) {
+          const double2 pv = __ldcg(reinterpret_cast<const double2*>(a.pyv) + g);
+          y0 += pv.x;
+          y1 += pv.y;
+        }
+        y0 = warp_sum(y0);
+        y1 = warp_sum(y1);
+        if (lane == 0) {
+          s_yv = mk(y0, y1);
+          s_ypiv = ypiv;
+        }
       }
       __syncthreads();
+      PT_MARK(0);
       if (tid < 32) {  // one warp: Re(cw^H cv) and the pivot-row correction sum
         double re = 0.0;
         cplx acc = mk(0, 0);
@@ -171,38 +263,41 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       const int ip = pw - 1;
       const int cp = p0 + ip;
       const cplx taup = s_tau_prev, alphap = s_alpha_prev;
-      for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+      int sidx = 0;
+      for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
         const int r = p0 + s * RS + rr;
         const bool act = (r < n) && (r >= cp + 1);
         cplx acc = mk(0, 0);
         if (act) {
           for (int k = cl; k < ip; k += 16) {
-            cfma(acc, Vp[(long)k * a.ldp + r], scw[k]);
-            cfma(acc, Wp[(long)k * a.ldp + r], scv[k]);
+            cfma(acc, ldV(sidx, k, r), scw[k]);
+            cfma(acc, ldW(sidx, k, r), scv[k]);
           }
         }
         const cplx tot = reduce_cl(acc, sred);
         if (cl == 0 && act) {
-          const cplx y = Yp[(long)ip * a.ldp + r];
-          const cplx v = Vp[(long)ip * a.ldp + r];
+          const cplx y = sidx < smax ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r];
+          const cplx v = ldV(sidx, ip, r);
           Wp[(long)ip * a.ldp + r] = cadd(cmul(taup, csub(y, tot)), cmul(alphap, v));
         }
       }
       break;
     }
-    PT_MARK(0);
+    PT_MARK(1);
     double nrm = 0.0;
     {
       const int ip = i - 1;
       const cplx taup = s_tau_prev, alphap = s_alpha_prev;
-      for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+      int sidx = 0;
+      for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
         const int r = p0 + s * RS + rr;
         const bool act = (r < n) && (r >= c);
         cplx acc1 = mk(0, 0), acc2 = mk(0, 0);
         if (act && i > 0) {
+#pragma unroll 4
           for (int k = cl; k < ip; k += 16) {
-            const cplx v = Vp[(long)k * a.ldp + r];
-            const cplx w = Wp[(long)k * a.ldp + r];
+            const cplx v = ldV(sidx, k, r);
+            const cplx w = ldW(sidx, k, r);
             cfma(acc1, v, scw[k]);
             cfma(acc1, w, scv[k]);
             cfma(acc2, v, cconj(pivW[k]));
@@ -211,12 +306,16 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         }
         if (i > 0) reduce_cl2(acc1, acc2, sred);
         if (cl == 0 && act) {
-          cplx av = a.A[(long)c * a.lda + r];
+          const bool res = sidx < smax;
+          // the column was prefetched into shared memory during the previous column's phase B (it is not modified
+          // inside this launch before this point)
+          cplx av = (res && i > 0) ? sres[sidx * SB + 2 * PW * RS + RS + rr] : a.A[(long)c * a.lda + r];
           if (i > 0) {
-            const cplx y = Yp[(long)ip * a.ldp + r];
-            const cplx v = Vp[(long)ip * a.ldp + r];
+            const cplx y = res ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r];
+            const cplx v = ldV(sidx, ip, r);
             const cplx wf = cadd(cmul(taup, csub(y, acc1)), cmul(alphap, v));
             Wp[(long)ip * a.ldp + r] = wf;
+            if (res) sres[sidx * SB + (PW + ip) * RS + rr] = wf;
             cfma(acc2, v, cconj(pivW[ip]));
             cfma(acc2, wf, cconj(pivV[ip]));
             av = csub(av, acc2);
@@ -226,15 +325,15 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         }
       }
     }
+    PT_MARK(2);
     {
       double v1[1] = {nrm};
       block_sum<1>(v1, sblk);
-      if (tid == 0 && v1[0] != 0.0) atomicAdd(&a.acc_norm[i], v1[0]);
+      if (tid == 0) a.pnorm[blockIdx.x] = v1[0];
     }
-    PT_MARK(1);
-    epoch += gridDim.x;
-    grid_bar(a.bar, epoch);
-    PT_MARK(2);
+    PT_MARK(3);
+    grid_bar(a.arrive, a.release, ++epoch);
+    PT_MARK(4);
     // ---------------- phase B: reflector, v, y = A22 v, panel dots ----------------
     const int nv = n - (c + 1);
     // software pipelining across the scalar phase: the first 8 trailing-matrix loads of this CTA's first strip do not
@@ -249,12 +348,25 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         pre[u] = (act0 && j < n) ? a.A[(long)j * a.lda + r0] : mk(0, 0);
       }
     }
-    const double xn2 = __ldcg(&a.acc_norm[i]);
     const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
+    if (tid >= NT - 32) {  // |x|^2 from the per-CTA partials
+      const int lane = tid - (NT - 32);
+      double x = 0.0;
+      for (int g = lane; g < (int)gridDim.x; g += 32) x += __ldcg(&a.pnorm[g]);
+      x = warp_sum(x);
+      if (lane == 0) s_xn2 = x;
+    }
     {
       // scalars and the raw column are fetched in one round of independent loads; scaling happens in shared memory
       const cplx* colp = a.A + (long)c * a.lda + c + 1;
       int j = tid;
+      for (; j + 7 * NT < nv; j += 8 * NT) {
+        cplx x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = ldcg_c(colp + j + u * NT);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sv[j + u * NT] = x[u];
+      }
       for (; j + 3 * NT < nv; j += 4 * NT) {
         const cplx x0 = ldcg_c(colp + j), x1 = ldcg_c(colp + j + NT), x2 = ldcg_c(colp + j + 2 * NT),
                    x3 = ldcg_c(colp + j + 3 * NT);
@@ -265,6 +377,9 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       }
       for (; j < nv; j += NT) sv[j] = ldcg_c(colp + j);
     }
+    __syncthreads();
+    PT_MARK(5);
+    const double xn2 = s_xn2;
     double beta;
     cplx tau, scal;
     if (xn2 == 0.0 && alpha.y == 0.0) {
@@ -284,18 +399,23 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       a.e[c] = beta;
       a.taus[c] = tau;
     }
-    __syncthreads();
     for (int j = tid; j < nv; j += NT) sv[j] = (j == 0) ? mk(1, 0) : cmul(sv[j], scal);
     __syncthreads();
-    PT_MARK(3);
+    PT_MARK(6);
     cplx cwa[PW / 16], cva[PW / 16];
 #pragma unroll
     for (int q = 0; q < PW / 16; ++q) cwa[q] = cva[q] = mk(0, 0);
     double yv0 = 0.0, yv1 = 0.0;
-    for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+    bool has_rows = false;
+    int sidx = 0;
+    for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
       const int r = p0 + s * RS + rr;
       const bool act = (r < n) && (r >= c + 1);
+      has_rows = has_rows || (p0 + s * RS + RS - 1 >= c + 1);  // uniform over the CTA
       cplx acc = mk(0, 0);
+      // next column of the own rows, consumed by phase A of column i+1 (untouched by this launch so far)
+      cplx anext = mk(0, 0);
+      if (cl == 0 && act && sidx < smax && i + 1 < pw) anext = a.A[(long)(c + 1) * a.lda + r];
       if (act) {
         const cplx* arow = a.A + r;
         // 8 independent 16-byte loads in flight per thread (the HEMV is latency/L2-bandwidth bound)
@@ -332,8 +452,8 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         for (int q = 0; q < PW / 16; ++q) {
           const int k = cl + 16 * q;
           if (k < i) {
-            cfma_conj(cwa[q], Wp[(long)k * a.ldp + r], vr);
-            cfma_conj(cva[q], Vp[(long)k * a.ldp + r], vr);
+            cfma_conj(cwa[q], ldW(sidx, k, r), vr);
+            cfma_conj(cva[q], ldV(sidx, k, r), vr);
           }
         }
       }
@@ -342,11 +462,16 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         const cplx vr = sv[r - c - 1];
         Vp[(long)i * a.ldp + r] = vr;
         Yp[(long)i * a.ldp + r] = y;
+        if (sidx < smax) {
+          sres[sidx * SB + i * RS + rr] = vr;
+          sres[sidx * SB + 2 * PW * RS + rr] = y;
+          sres[sidx * SB + 2 * PW * RS + RS + rr] = anext;
+        }
         yv0 += y.x * vr.x + y.y * vr.y;
         yv1 += y.x * vr.y - y.y * vr.x;
       }
     }
-    PT_MARK(4);
+    PT_MARK(7);
     // reduce the panel dots over the 16 rows of the half-warp, then one atomic per (k, CTA)
 #pragma unroll
     for (int q = 0; q < PW / 16; ++q) {
@@ -360,25 +485,24 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         x3 += __shfl_xor_sync(0xffffffffu, x3, o);
       }
       const int k = cl + 16 * q;
-      if (rr == 0 && k < i) {
-        atomicAdd(&a.acc_cw[2 * (i * PW + k)], x0);
-        atomicAdd(&a.acc_cw[2 * (i * PW + k) + 1], x1);
-        atomicAdd(&a.acc_cv[2 * (i * PW + k)], x2);
-        atomicAdd(&a.acc_cv[2 * (i * PW + k) + 1], x3);
+      if (rr == 0 && k < i && has_rows) {
+        double* cw = a.acc_cw + (long)(blockIdx.x % NREP) * 2 * PW * PW + 2 * (i * PW + k);
+        double* cv = a.acc_cv + (long)(blockIdx.x % NREP) * 2 * PW * PW + 2 * (i * PW + k);
+        atomicAdd(cw, x0);
+        atomicAdd(cw + 1, x1);
+        atomicAdd(cv, x2);
+        atomicAdd(cv + 1, x3);
       }
     }
+    PT_MARK(8);
     {
       double v2[2] = {yv0, yv1};
       block_sum<2>(v2, sblk);
-      if (tid == 0) {
-        atomicAdd(&a.acc_yv[2 * i], v2[0]);
-        atomicAdd(&a.acc_yv[2 * i + 1], v2[1]);
-      }
+      if (tid == 0) reinterpret_cast<double2*>(a.pyv)[blockIdx.x] = make_double2(v2[0], v2[1]);
     }
-    PT_MARK(5);
-    epoch += gridDim.x;
-    grid_bar(a.bar, epoch);
-    PT_MARK(6);
+    PT_MARK(9);
+    grid_bar(a.arrive, a.release, ++epoch);
+    PT_MARK(10);
   }
   // ---------------- panel epilogue: build [V|W], [W|V], store reflectors into A ----------------
   __syncthreads();
@@ -468,9 +592,9 @@ __global__ void gather_real_cols_kernel(int n, int k, const double* __restrict__
 #ifdef TEVO_PANEL_TIMING
 extern "C" int tevo_debug_panel_cycles(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, g_panel_cycles, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(out, g_panel_cycles, sizeof(unsigned long long) * 16);
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(g_panel_cycles, z, sizeof(z));
   }
   return 0;
@@ -481,7 +605,8 @@ void Heig::init() {
   int dev = 0;
   TEVO_CUDA_CHECK(cudaGetDevice(&dev));
   TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
-  TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (PW + 2 * PW + 4 * PW * PW + 8)));
+  // [pnorm MAXCTA | pyv 2*MAXCTA | arrive, release: MAXCTA lines each | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
+  TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (3 * MAXCTA + 2 * MAXCTA * 16 + 2 * NREP * 2 * PW * PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&Tblk_, sizeof(cplx) * PW * PW));
 }
 
@@ -529,31 +654,37 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   lda_ = lda;
   static std::once_flag once;
   std::call_once(once, [&]() {
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16));
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * sizeof(cplx) * TRB * TRB)));
   });
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
-  double* acc_norm = acc_;
-  double* acc_yv = acc_ + PW;
-  double* acc_cw = acc_ + 3 * PW;
+  double* zero_from = acc_ + 3 * MAXCTA;  // flags and the replicated accumulators are cleared before every panel
+  const size_t zero_bytes = sizeof(double) * (2 * MAXCTA * 16 + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
   TEVO_CUDA_CHECK(cudaMemsetAsync(Sall_, 0, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW), st));
   int p0 = 0;
   while (p0 < n - 1) {
     const int pw = std::min(PW, n - 1 - p0);
-    TEVO_CUDA_CHECK(cudaMemsetAsync(acc_, 0, sizeof(double) * (PW + 2 * PW + 4 * PW * PW + 8), st));
+    TEVO_CUDA_CHECK(cudaMemsetAsync(zero_from, 0, zero_bytes, st));
     PanelArgs pa;
     pa.n = n; pa.p0 = p0; pa.pw = pw; pa.A = A; pa.lda = lda; pa.P = P_; pa.Q = Q_; pa.Y = Y_; pa.ldp = n;
-    pa.acc_norm = acc_norm; pa.acc_yv = acc_yv; pa.acc_cw = acc_cw;
-    pa.acc_cv = Sall_ + (size_t)(p0 / PW) * 2 * PW * PW;
-    pa.bar = reinterpret_cast<unsigned*>(acc_ + PW + 2 * PW + 4 * PW * PW);
+    pa.pnorm = acc_; pa.pyv = acc_ + MAXCTA;
+    pa.arrive = reinterpret_cast<unsigned*>(zero_from);
+    pa.release = reinterpret_cast<unsigned*>(zero_from + MAXCTA * 16);
+    pa.acc_cw = zero_from + 2 * MAXCTA * 16;
+    pa.acc_cv = pa.acc_cw + NREP * 2 * PW * PW;
+    pa.cv_out = Sall_ + (size_t)(p0 / PW) * 2 * PW * PW;
     pa.d = d_; pa.e = e_; pa.taus = taus_;
     const int nstrips = (n - p0 + RS - 1) / RS;
     const int cap = (max_ctas_ > 0) ? std::min(max_ctas_, num_sms_) : num_sms_;
-    const int grid = std::max(1, std::min(cap, nstrips));
+    const int grid = std::max(1, std::min(std::min(cap, MAXCTA), nstrips));
     void* args[] = {&pa};
-    const size_t smem = (size_t)(n - p0) * sizeof(cplx);
+    const size_t sv_bytes = (size_t)((n - p0 + 1) & ~1) * sizeof(cplx);
+    const size_t strip_bytes = (size_t)(2 * PW * RS + 2 * RS) * sizeof(cplx);
+    const int per_cta = (nstrips + grid - 1) / grid;
+    pa.smax = std::min(per_cta, (int)((PANEL_SMEM - sv_bytes) / strip_bytes));
+    const size_t smem = sv_bytes + (size_t)pa.smax * strip_bytes;
     {
       ProfScope ps(st, P_TRI_PANEL);
       TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)tridiag_panel_kernel, dim3(grid), dim3(NT), args, smem, st));
@@ -562,7 +693,7 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     // compact-WY factor and V*T for the back-transformation
     {
       ProfScope ps(st, P_TRI_WY);
-      wy_T_kernel<<<1, 1024, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.acc_cv, Tblk_);
+      wy_T_kernel<<<1, 1024, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.cv_out, Tblk_);
       TEVO_LAUNCHED();
       zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
     }
