@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtevo.so")
+LIB_PATH = os.environ.get("TEVO_LIB") or os.path.join(_HERE, "libtevo.so")
 
 TEVO_OK, TEVO_EINVAL, TEVO_ECUDA, TEVO_ENOMEM, TEVO_ENOTCONVERGED, TEVO_EINTERNAL = range(6)
 

@@ -6,6 +6,7 @@
 #include "heig.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "prof.h"
 #include "trinv.cuh"
@@ -23,7 +24,9 @@ constexpr int MAXCTA = 256;    // slots of the per-CTA arrays (flags, partial no
 
 struct PanelArgs {
   int n, p0, pw;
-  int smax;  // strips per CTA whose rows of V, W (and y, next column) are kept in shared memory
+  int smax;    // strips per CTA whose rows of V, W (and y, next column) are kept in shared memory
+  int chunks;  // column chunks per strip: CTA b works on strip b % nstrips, chunk b / nstrips (1: CTA b owns strips b, b+G, ..)
+  int ncache;  // 16-column groups of the CTA's trailing-matrix slice kept in shared memory for the whole panel
   cplx* A;
   long lda;
   cplx* P;  // n x 2*PW : [V | W]
@@ -159,11 +162,14 @@ __device__ inline cplx reduce_cl(cplx v, cplx* sred) {
 //               dots W^H v, V^H v and y^H v (w^H v follows algebraically, so w needs no third reduction) -> barrier
 __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  cplx* sv = reinterpret_cast<cplx*>(smraw);  // v (n - p0 entries max)
+  // v (at most n - p0 entries) with 16 zero entries in front and behind: the HEMV walks whole 16-column groups and
+  // lets the columns <= c / >= n of the first / last group multiply zeros instead of testing every element
+  cplx* sv = reinterpret_cast<cplx*>(smraw) + 16;
   // resident copies of the own rows: per strip [V: PW x RS | W: PW x RS | y: RS | next column: RS]
   constexpr int SB = 2 * PW * RS + 2 * RS;
-  cplx* sres = sv + ((a.n - a.p0 + 1) & ~1);
+  cplx* sres = sv + ((a.n - a.p0 + 1) & ~1) + 16;
   const int smax = a.smax;
+  cplx* sAc = sres + smax * SB;  // resident part of the trailing-matrix slice: [group][thread]
   __shared__ cplx sred[2 * NT];
   __shared__ cplx pivV[PW], pivW[PW], scw[PW], scv[PW];
   __shared__ cplx s_tau_prev, s_alpha_prev, s_yv, s_ypiv;
@@ -172,6 +178,23 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   const int n = a.n, p0 = a.p0, pw = a.pw;
   const int tid = threadIdx.x, rr = tid % RS, cl = tid / RS;
   const int nstrips = (n - p0 + RS - 1) / RS;
+  // work split: rows in 16-row strips; if there are fewer strips than CTAs the columns of a strip are split into
+  // `chunks` interleaved sets of 16-column groups and the partial y are combined with atomics.  Chunk 0 owns the strip
+  // (phase A, panel dots, V/W rows), chunks > 0 only help with the HEMV.
+  const int chunks = a.chunks;
+  const int my_q = blockIdx.x / nstrips;
+  const int s_first = blockIdx.x % nstrips;
+  const int s_step = (chunks > 1) ? nstrips : (int)gridDim.x;
+  const bool helper = my_q > 0;
+  const int own_first = helper ? nstrips : s_first;
+  const int NGL = (nstrips - my_q + chunks - 1) / chunks;          // 16-column groups of this CTA: g = my_q + chunks*gl
+  const int glc = (a.ncache > 0) ? max(NGL - a.ncache, 0) : NGL;  // groups gl >= glc are resident in shared memory
+  const long jstep = 16L * chunks;
+  // streamed groups stop before the last group of the matrix if that one is partial (n not a multiple of 16)
+  const int NGf = (n - p0) / 16;
+  const int NGLf = (NGf > my_q) ? (NGf - my_q + chunks - 1) / chunks : 0;
+  const int glcs = min(glc, NGLf);
+  const bool tail_streamed = (NGLf < NGL) && (NGLf < glc);
   cplx* Vp = a.P;
   cplx* Wp = a.P + (long)PW * a.ldp;
   cplx* Yp = a.Y;
@@ -188,6 +211,23 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   long long _t0 = clock64();
 #endif
 
+  if (tid < 16) sv[tid - 16] = mk(0, 0);
+  if (a.ncache > 0) {
+    // the trailing matrix is not modified inside a panel (columns > c are read, column c is written): keep the last
+    // groups of this CTA's slice on chip for all pw columns
+    const int r = p0 + s_first * RS + rr;
+    for (int gl = glc; gl < NGL; gl += 8) {
+      cplx x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = p0 + 16 * (my_q + chunks * (gl + u)) + cl;
+        x[u] = (gl + u < NGL && r < n && j < n) ? a.A[(long)j * a.lda + r] : mk(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (gl + u < NGL) sAc[(gl + u - glc) * NT + tid] = x[u];
+    }
+  }
   for (int i = 0; i <= pw; ++i) {
     const int c = p0 + i;
     // ---------------- phase A ----------------
@@ -264,7 +304,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       const int cp = p0 + ip;
       const cplx taup = s_tau_prev, alphap = s_alpha_prev;
       int sidx = 0;
-      for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
+      for (int s = own_first; s < nstrips; s += s_step, ++sidx) {
         const int r = p0 + s * RS + rr;
         const bool act = (r < n) && (r >= cp + 1);
         cplx acc = mk(0, 0);
@@ -276,7 +316,8 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         }
         const cplx tot = reduce_cl(acc, sred);
         if (cl == 0 && act) {
-          const cplx y = sidx < smax ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r];
+          const cplx y = (chunks > 1) ? ldcg_c(&Yp[(long)ip * a.ldp + r])
+                                      : (sidx < smax ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r]);
           const cplx v = ldV(sidx, ip, r);
           Wp[(long)ip * a.ldp + r] = cadd(cmul(taup, csub(y, tot)), cmul(alphap, v));
         }
@@ -289,7 +330,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       const int ip = i - 1;
       const cplx taup = s_tau_prev, alphap = s_alpha_prev;
       int sidx = 0;
-      for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
+      for (int s = own_first; s < nstrips; s += s_step, ++sidx) {
         const int r = p0 + s * RS + rr;
         const bool act = (r < n) && (r >= c);
         cplx acc1 = mk(0, 0), acc2 = mk(0, 0);
@@ -311,7 +352,8 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
           // inside this launch before this point)
           cplx av = (res && i > 0) ? sres[sidx * SB + 2 * PW * RS + RS + rr] : a.A[(long)c * a.lda + r];
           if (i > 0) {
-            const cplx y = res ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r];
+            const cplx y = (chunks > 1) ? ldcg_c(&Yp[(long)ip * a.ldp + r])
+                                        : (res ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r]);
             const cplx v = ldV(sidx, ip, r);
             const cplx wf = cadd(cmul(taup, csub(y, acc1)), cmul(alphap, v));
             Wp[(long)ip * a.ldp + r] = wf;
@@ -322,6 +364,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
             a.A[(long)c * a.lda + r] = av;
           }
           if (r >= c + 2) nrm += cabs2(av);
+          if (chunks > 1) Yp[(long)i * a.ldp + r] = mk(0, 0);  // the chunks add their partial y in phase B
         }
       }
     }
@@ -338,14 +381,16 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     const int nv = n - (c + 1);
     // software pipelining across the scalar phase: the first 8 trailing-matrix loads of this CTA's first strip do not
     // depend on v, so they are issued now and consumed by the HEMV below
+    const int g_min = (c + 1 - p0) >> 4;  // first group with a column > c
+    const int gl0 = (g_min <= my_q) ? 0 : (g_min - my_q + chunks - 1) / chunks;
     cplx pre[8];
     {
-      const int r0 = p0 + blockIdx.x * RS + rr;
+      const int r0 = p0 + s_first * RS + rr;
       const bool act0 = (r0 < n) && (r0 >= c + 1);
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int j = c + 1 + cl + 16 * u;
-        pre[u] = (act0 && j < n) ? a.A[(long)j * a.lda + r0] : mk(0, 0);
+        const int j = p0 + 16 * (my_q + chunks * (gl0 + u)) + cl;
+        pre[u] = (act0 && gl0 + u < glcs) ? a.A[(long)j * a.lda + r0] : mk(0, 0);
       }
     }
     const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
@@ -400,6 +445,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       a.taus[c] = tau;
     }
     for (int j = tid; j < nv; j += NT) sv[j] = (j == 0) ? mk(1, 0) : cmul(sv[j], scal);
+    if (tid < 16) sv[nv + tid] = mk(0, 0);
     __syncthreads();
     PT_MARK(6);
     cplx cwa[PW / 16], cva[PW / 16];
@@ -408,64 +454,97 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     double yv0 = 0.0, yv1 = 0.0;
     bool has_rows = false;
     int sidx = 0;
-    for (int s = blockIdx.x; s < nstrips; s += gridDim.x, ++sidx) {
+    for (int s = s_first; s < nstrips; s += s_step, ++sidx) {
       const int r = p0 + s * RS + rr;
       const bool act = (r < n) && (r >= c + 1);
-      has_rows = has_rows || (p0 + s * RS + RS - 1 >= c + 1);  // uniform over the CTA
+      has_rows = has_rows || (!helper && p0 + s * RS + RS - 1 >= c + 1);  // uniform over the CTA
       cplx acc = mk(0, 0);
       // next column of the own rows, consumed by phase A of column i+1 (untouched by this launch so far)
       cplx anext = mk(0, 0);
-      if (cl == 0 && act && sidx < smax && i + 1 < pw) anext = a.A[(long)(c + 1) * a.lda + r];
+      if (cl == 0 && act && !helper && sidx < smax && i + 1 < pw) anext = a.A[(long)(c + 1) * a.lda + r];
       if (act) {
         const cplx* arow = a.A + r;
-        // 8 independent 16-byte loads in flight per thread (the HEMV is latency/L2-bandwidth bound)
         cplx ac[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) ac[u] = mk(0, 0);
-        int j = c + 1 + cl;
-        if (s == (int)blockIdx.x) {  // prefetched columns (zero beyond the matrix edge)
+        const int jb0 = p0 + 16 * my_q + cl;  // column of local group gl: jb0 + jstep * gl
+        const cplx* svb = sv - c - 1;          // v_j = svb[j]; zero for c - 15 <= j <= c and n <= j < n + 16
+        const long astep = jstep * a.lda;
+        int gl = gl0;
+        if (sidx == 0) {  // prefetched groups
 #pragma unroll
           for (int u = 0; u < 8; ++u)
-            if (j + 16 * u < n) cfma(ac[u & 3], pre[u], sv[j + 16 * u - c - 1]);
-          j += 16 * 8;
+            if (gl0 + u < glcs) cfma(ac[u & 3], pre[u], svb[jb0 + (int)jstep * (gl0 + u)]);
+          gl += 8;
         }
-        for (; j + 16 * 15 < n; j += 16 * 16) {
+        // streamed groups (L2): 16 independent 16-byte loads in flight per thread, no per-element tests
+        for (; gl + 15 < glcs; gl += 16) {
           cplx av[16];
+          const cplx* ap = arow + (long)(jb0 + (int)jstep * gl) * a.lda;
+          const cplx* vp = svb + jb0 + (int)jstep * gl;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
+          for (int u = 0; u < 16; ++u) av[u] = ap[u * astep];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) cfma(ac[u & 3], av[u], sv[j + 16 * u - c - 1]);
+          for (int u = 0; u < 16; ++u) cfma(ac[u & 3], av[u], vp[u * (int)jstep]);
         }
-        for (; j + 16 * 3 < n; j += 16 * 4) {
+        for (; gl + 3 < glcs; gl += 4) {
           cplx av[4];
+          const cplx* ap = arow + (long)(jb0 + (int)jstep * gl) * a.lda;
+          const cplx* vp = svb + jb0 + (int)jstep * gl;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) av[u] = arow[(long)(j + 16 * u) * a.lda];
+          for (int u = 0; u < 4; ++u) av[u] = ap[u * astep];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) cfma(ac[u], av[u], sv[j + 16 * u - c - 1]);
+          for (int u = 0; u < 4; ++u) cfma(ac[u], av[u], vp[u * (int)jstep]);
         }
-        for (; j < n; j += 16) cfma(ac[0], arow[(long)j * a.lda], sv[j - c - 1]);
+        for (; gl < glcs; ++gl) {
+          const int j = jb0 + (int)jstep * gl;
+          cfma(ac[0], arow[(long)j * a.lda], svb[j]);
+        }
+        if (tail_streamed && NGLf >= gl0) {  // the last, partial group of the matrix (n not a multiple of 16)
+          const int j = jb0 + (int)jstep * NGLf;
+          if (j < n) cfma(ac[1], arow[(long)j * a.lda], svb[j]);
+        }
+        // resident groups (shared memory; only CTAs with a single strip have any; columns >= n are stored as zeros)
+        int gc = max(gl0, glc);
+        for (; gc + 3 < NGL; gc += 4) {
+          const cplx* vp = svb + jb0 + (int)jstep * gc;
+          const cplx* cp = sAc + (gc - glc) * NT + tid;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cfma(ac[u], cp[u * NT], vp[u * (int)jstep]);
+        }
+        for (; gc < NGL; ++gc) cfma(ac[0], sAc[(gc - glc) * NT + tid], svb[jb0 + (int)jstep * gc]);
 #pragma unroll
         for (int u = 1; u < 4; ++u) ac[0] = cadd(ac[0], ac[u]);
         acc = ac[0];
-        const cplx vr = sv[r - c - 1];
+        if (!helper) {
+          const cplx vr = sv[r - c - 1];
 #pragma unroll
-        for (int q = 0; q < PW / 16; ++q) {
-          const int k = cl + 16 * q;
-          if (k < i) {
-            cfma_conj(cwa[q], ldW(sidx, k, r), vr);
-            cfma_conj(cva[q], ldV(sidx, k, r), vr);
+          for (int q = 0; q < PW / 16; ++q) {
+            const int k = cl + 16 * q;
+            if (k < i) {
+              cfma_conj(cwa[q], ldW(sidx, k, r), vr);
+              cfma_conj(cva[q], ldV(sidx, k, r), vr);
+            }
           }
         }
       }
       const cplx y = reduce_cl(acc, sred);
       if (cl == 0 && act) {
         const cplx vr = sv[r - c - 1];
-        Vp[(long)i * a.ldp + r] = vr;
-        Yp[(long)i * a.ldp + r] = y;
-        if (sidx < smax) {
-          sres[sidx * SB + i * RS + rr] = vr;
-          sres[sidx * SB + 2 * PW * RS + rr] = y;
-          sres[sidx * SB + 2 * PW * RS + RS + rr] = anext;
+        if (!helper) {
+          Vp[(long)i * a.ldp + r] = vr;
+          if (sidx < smax) {
+            sres[sidx * SB + i * RS + rr] = vr;
+            sres[sidx * SB + 2 * PW * RS + RS + rr] = anext;
+          }
+        }
+        if (chunks > 1) {
+          double* yp = reinterpret_cast<double*>(&Yp[(long)i * a.ldp + r]);
+          atomicAdd(yp, y.x);
+          atomicAdd(yp + 1, y.y);
+        } else {
+          Yp[(long)i * a.ldp + r] = y;
+          if (sidx < smax) sres[sidx * SB + 2 * PW * RS + rr] = y;
         }
         yv0 += y.x * vr.x + y.y * vr.y;
         yv1 += y.x * vr.y - y.y * vr.x;
@@ -506,7 +585,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   }
   // ---------------- panel epilogue: build [V|W], [W|V], store reflectors into A ----------------
   __syncthreads();
-  for (int s = blockIdx.x; s < nstrips; s += gridDim.x) {
+  for (int s = own_first; s < nstrips; s += s_step) {
     for (int k = cl; k < pw; k += 16) {
       const int r = p0 + s * RS + rr;
       if (r >= n) continue;
@@ -532,8 +611,13 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
 // the upper-triangular M is inverted in shared memory (as the transpose of a lower-triangular inverse).
 // S holds (V^H v_l)_j for j < l at S[2*(l*PW + j)] (the panel kernel's acc_cv).  tau_j = 0 (identity reflector):
 // row and column j of T are zero.  T is written column-major PW x PW.
-__global__ void __launch_bounds__(1024) wy_T_kernel(int pw, const cplx* __restrict__ taus, const double* __restrict__ S,
-                                                   cplx* __restrict__ T) {
+// One CTA per panel: panel b covers columns b*PW .. of the n x n problem.
+__global__ void __launch_bounds__(1024) wy_T_kernel(int n, const cplx* __restrict__ taus_all,
+                                                   const double* __restrict__ S_all, cplx* __restrict__ T_all) {
+  const int pw = min(PW, n - 1 - (int)blockIdx.x * PW);
+  const cplx* taus = taus_all + (long)blockIdx.x * PW;
+  const double* S = S_all + (long)blockIdx.x * 2 * PW * PW;
+  cplx* T = T_all + (long)blockIdx.x * PW * PW;
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx(*a)[TRB] = reinterpret_cast<cplx(*)[TRB]>(smraw);  // a[p][i] = M^T(i,p) = M(p,i)
   cplx(*x)[TRB] = a + TRB;
@@ -607,7 +691,6 @@ void Heig::init() {
   TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
   // [pnorm MAXCTA | pyv 2*MAXCTA | arrive, release: MAXCTA lines each | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
   TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (3 * MAXCTA + 2 * MAXCTA * 16 + 2 * NREP * 2 * PW * PW)));
-  TEVO_CUDA_CHECK(cudaMalloc(&Tblk_, sizeof(cplx) * PW * PW));
 }
 
 void Heig::destroy() {
@@ -629,8 +712,9 @@ void Heig::ensure(int n) {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_); fr(Tblk_);
   const size_t nn = (size_t)n * n;
+  TEVO_CUDA_CHECK(cudaMalloc(&Tblk_, sizeof(cplx) * PW * PW * (size_t)((n + PW - 1) / PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&P_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Q_, sizeof(cplx) * (size_t)n * 2 * PW));
   TEVO_CUDA_CHECK(cudaMalloc(&Y_, sizeof(cplx) * (size_t)n * PW));
@@ -638,7 +722,7 @@ void Heig::ensure(int n) {
   TEVO_CUDA_CHECK(cudaMalloc(&VT_, sizeof(cplx) * nn));
   TEVO_CUDA_CHECK(cudaMalloc(&d_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&e_, sizeof(double) * n));
-  TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * ((size_t)n + PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&evals_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&Z_, sizeof(double) * nn));
   TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * n));
@@ -677,25 +761,39 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     pa.cv_out = Sall_ + (size_t)(p0 / PW) * 2 * PW * PW;
     pa.d = d_; pa.e = e_; pa.taus = taus_;
     const int nstrips = (n - p0 + RS - 1) / RS;
-    const int cap = (max_ctas_ > 0) ? std::min(max_ctas_, num_sms_) : num_sms_;
-    const int grid = std::max(1, std::min(std::min(cap, MAXCTA), nstrips));
+    static const int env_cap = [] {
+      const char* e = getenv("TEVO_PANEL_MAX_CTAS");  // development knob: forces the multi-strip work split
+      return e ? atoi(e) : 0;
+    }();
+    int cap = (max_ctas_ > 0) ? std::min(max_ctas_, num_sms_) : num_sms_;
+    if (env_cap > 0) cap = std::min(cap, env_cap);
+    const int capc = std::max(1, std::min(cap, MAXCTA));
+    int grid = capc, chunks = 1;
+    if (nstrips < capc) {  // fewer strips than SMs: split the columns of a strip (>= 8 groups of 16 columns per chunk)
+      chunks = std::max(1, std::min(capc / nstrips, nstrips / 8));
+      grid = nstrips * chunks;
+    }
+    pa.chunks = chunks;
     void* args[] = {&pa};
-    const size_t sv_bytes = (size_t)((n - p0 + 1) & ~1) * sizeof(cplx);
+    const size_t sv_bytes = (size_t)(((n - p0 + 1) & ~1) + 32) * sizeof(cplx);
     const size_t strip_bytes = (size_t)(2 * PW * RS + 2 * RS) * sizeof(cplx);
     const int per_cta = (nstrips + grid - 1) / grid;
-    pa.smax = std::min(per_cta, (int)((PANEL_SMEM - sv_bytes) / strip_bytes));
-    const size_t smem = sv_bytes + (size_t)pa.smax * strip_bytes;
+    static const size_t panel_smem = [] {
+      const char* e = getenv("TEVO_PANEL_SMEM");  // development knob: shared-memory budget in bytes
+      return e ? std::min<size_t>(PANEL_SMEM, (size_t)atol(e)) : (size_t)PANEL_SMEM;
+    }();
+    pa.smax = std::min(per_cta, (int)((panel_smem - sv_bytes) / strip_bytes));
+    size_t smem = sv_bytes + (size_t)pa.smax * strip_bytes;
+    pa.ncache = 0;
+    if (per_cta == 1) {
+      const int groups_per_cta = (nstrips + chunks - 1) / chunks;
+      pa.ncache = (panel_smem > smem) ? std::min(groups_per_cta, (int)((panel_smem - smem) / (NT * sizeof(cplx)))) : 0;
+      smem += (size_t)pa.ncache * NT * sizeof(cplx);
+    }
     {
       ProfScope ps(st, P_TRI_PANEL);
       TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)tridiag_panel_kernel, dim3(grid), dim3(NT), args, smem, st));
       TEVO_LAUNCHED();
-    }
-    // compact-WY factor and V*T for the back-transformation
-    {
-      ProfScope ps(st, P_TRI_WY);
-      wy_T_kernel<<<1, 1024, 2 * sizeof(cplx) * TRB * TRB, st>>>(pw, taus_ + p0, pa.cv_out, Tblk_);
-      TEVO_LAUNCHED();
-      zgemm(st, OP_N, OP_N, n - p0, pw, pw, ONE, A + (long)p0 * lda + p0, lda, Tblk_, PW, ZERO, VT_ + (long)p0 * n + p0, n);
     }
     const int q0 = p0 + pw;
     // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H
@@ -711,6 +809,23 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   }
   last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
   TEVO_LAUNCHED();
+  if (n > 1) {
+    // compact-WY factors of all panels in one launch, then V*T for the back-transformation as one batched GEMM over
+    // the full-width panels (A holds V with explicit zeros above the reflectors) plus one for a narrower last panel
+    ProfScope ps(st, P_TRI_WY);
+    const int npanels = (n - 1 + PW - 1) / PW;
+    wy_T_kernel<<<npanels, 1024, 2 * sizeof(cplx) * TRB * TRB, st>>>(n, taus_, Sall_, Tblk_);
+    TEVO_LAUNCHED();
+    const int nfull = n / PW;  // panels whose PW columns all exist
+    if (nfull > 0)
+      zgemm_batched(st, OP_N, OP_N, n, PW, PW, ONE, A, lda, (long)PW * lda, Tblk_, PW, (long)PW * PW, ZERO, VT_, n,
+                    (long)PW * n, nfull);
+    if (nfull < npanels) {
+      const int q0 = nfull * PW;
+      zgemm(st, OP_N, OP_N, n, n - q0, n - q0, ONE, A + (long)q0 * lda, lda, Tblk_ + (long)nfull * PW * PW, PW, ZERO,
+            VT_ + (long)q0 * n, n);
+    }
+  }
   {
     ProfScope ps(st, P_STEDC);
     stedc_.run(st, n, d_, e_, evals_, Z_);
