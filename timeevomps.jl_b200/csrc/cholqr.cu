@@ -26,26 +26,26 @@ __global__ void __launch_bounds__(1024) potrf_block_kernel(int nb, const cplx* _
                                                            cplx* __restrict__ Xm, long ld, double* __restrict__ stats) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx(*a)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw);  // a[p][i] = L(i,p)   (column p contiguous over rows i)
-  cplx(*x)[NB] = a + NB;                                // x[p][c] = inv(L)(p,c)
+  cplx(*x)[NB] = a + NB;                                // x[c][i] = inv(L)(i,c) up to the deferred row scaling
   const int tid = threadIdx.x;
   for (int e = tid; e < NB * NB; e += blockDim.x) {
     const int r = e % NB, p = e / NB;
     a[p][r] = (r < nb && p < nb) ? G[(long)p * ld + r] : mk(r == p ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
+  __shared__ double sinv[NB];
   double pmin, pmax;
-  if (!chol_lower_smem(a, nb, pmin, pmax)) {
+  if (!chol_inv_lower_smem(a, x, sinv, nb, pmin, pmax)) {
     if (tid == 0) {
       stats[0] = -1.0;
       stats[1] = 0.0;
     }
     return;
   }
-  trinv_lower_smem(a, x, nb);
   for (int e = tid; e < nb * nb; e += blockDim.x) {
     const int r = e % nb, p = e / nb;
-    Lm[(long)p * ld + r] = (r >= p) ? a[p][r] : mk(0, 0);
-    Xm[(long)p * ld + r] = (r >= p) ? x[r][p] : mk(0, 0);
+    Lm[(long)p * ld + r] = (r > p) ? cscale(sinv[p], a[p][r]) : (r == p ? mk(a[p][p].x * sinv[p], 0.0) : mk(0, 0));
+    Xm[(long)p * ld + r] = (r >= p) ? cscale(sinv[r], x[p][r]) : mk(0, 0);
   }
   if (tid == 0) {
     stats[0] = pmin;

@@ -54,4 +54,41 @@ __device__ inline void trinv_lower_smem(cplx (*a)[TRB], cplx (*x)[TRB], int nb) 
   }
 }
 
+// Cholesky factor and its inverse in one right-looking sweep with a single barrier per column.  The pivot scaling is
+// deferred: column k of `a` and row k of inv(L) stay unscaled (they are final once step k has read them) and the
+// updates divide by the pivot instead; sinv[k] = 1/L(k,k) is applied by the caller:
+//   L(i,k) = a[k][i] * sinv[k] (i >= k),   inv(L)(i,c) = xt[c][i] * sinv[i] (c <= i).
+// a[p][i] = A(i,p), Hermitian positive definite, lower part referenced; xt is the inverse stored by columns (thread
+// i works on row i of both matrices, so both are laid out with i contiguous: no bank conflicts).  Called by all
+// threads (blockDim.x a multiple of 64).  Returns false (uniformly) on a non-positive pivot; pmin/pmax: extremes of
+// L(k,k).
+__device__ inline bool chol_inv_lower_smem(cplx (*a)[TRB], cplx (*xt)[TRB], double* sinv, int nb, double& pmin,
+                                           double& pmax) {
+  pmin = 1e300;
+  pmax = 0.0;
+  for (int e = threadIdx.x; e < TRB * TRB; e += blockDim.x) {
+    const int i = e % TRB, c = e / TRB;
+    xt[c][i] = mk((i == c && i < nb) ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  const int i = threadIdx.x % TRB, tj = threadIdx.x / TRB, nj = blockDim.x / TRB;
+  for (int k = 0; k < nb; ++k) {
+    const double dkk = a[k][k].x;  // final: the update of step k-1 finished at the barrier below
+    if (!(dkk > 0.0) || !isfinite(dkk)) return false;
+    const double inv = rsqrt(dkk), l = dkk * inv, rd = inv * inv;
+    pmin = fmin(pmin, l);
+    pmax = fmax(pmax, l);
+    if (threadIdx.x == 0) sinv[k] = inv;
+    if (i > k && i < nb) {
+      const cplx aki = cscale(rd, a[k][i]);
+#pragma unroll 4
+      for (int j = k + 1 + tj; j <= i; j += nj) a[j][i] = csub(a[j][i], cmul(aki, cconj(a[k][j])));
+#pragma unroll 4
+      for (int c = tj; c <= k; c += nj) xt[c][i] = csub(xt[c][i], cmul(aki, xt[c][k]));
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
 }  // namespace tevo
