@@ -20,7 +20,7 @@ constexpr int RS = 16;  // rows per strip
 constexpr int NT = 256;
 constexpr int NREP = 8;        // replicas of the panel-dot accumulators (same-address L2 atomics serialise)
 constexpr int PANEL_SMEM = 200 * 1024;  // dynamic shared memory budget of the panel kernel
-constexpr int MAXCTA = 256;    // slots of the per-CTA arrays (flags, partial norms)
+constexpr int MAXCTA = 256;    // sanity cap on the cooperative grid
 
 struct PanelArgs {
   int n, p0, pw;
@@ -33,8 +33,7 @@ struct PanelArgs {
   cplx* Q;  // n x 2*PW : [W | V]
   cplx* Y;  // n x PW   : raw y = A22 v
   long ldp;
-  double* pnorm;     // per-CTA partial |x|^2 of the current column (rewritten every column, never zeroed)
-  double* pyv;       // per-CTA partial y^H v (2 doubles per CTA)
+  double* acc_yv;    // NREP x PW complex: y^H v, accumulated like the panel dots
   double* acc_cw;    // NREP x 2*PW*PW : W^H v, accumulated with atomics into replica blockIdx % NREP
   double* acc_cv;    // NREP x 2*PW*PW : V^H v
   double* cv_out;    // 2*PW*PW  (kept: V^H v, the strictly upper part of V^H V for the compact-WY T factor)
@@ -125,7 +124,6 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
   __shared__ cplx sred[2 * NT];
   __shared__ cplx pivV[PW], pivW[PW], scw[PW], scv[PW];
   __shared__ cplx s_tau_prev, s_alpha_prev, s_yv, s_ypiv;
-  __shared__ double s_xn2;
   __shared__ double sblk[64];
   const int n = a.n, p0 = a.p0, pw = a.pw;
   const int tid = threadIdx.x, rr = tid % RS, cl = tid / RS;
@@ -207,22 +205,15 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         }
         if (i < pw) pivV[k] = ldcg_c(&Vp[(long)k * a.ldp + c]);
       }
-      if (tid >= NT - 32) {  // another warp than the one that reduces below: y^H v from the per-CTA partials
-        const int lane = tid - (NT - 32);
-        cplx ypiv = mk(0, 0);
-        if (lane == 0 && i < pw) ypiv = ldcg_c(&Yp[(long)ip * a.ldp + c]);  // in flight with the partials below
-        double y0 = 0.0, y1 = 0.0;
-        for (int g = lane; g < (int)gridDim.x; g += 32) {
-          const double2 pv = __ldcg(reinterpret_cast<const double2*>(a.pyv) + g);
-          y0 += pv.x;
-          y1 += pv.y;
-        }
-        y0 = warp_sum(y0);
-        y1 = warp_sum(y1);
-        if (lane == 0) {
-          s_yv = mk(y0, y1);
-          s_ypiv = ypiv;
-        }
+      if (tid == NT - 1) {  // a thread of another warp than the one that reduces below
+        cplx y[NREP];
+#pragma unroll
+        for (int q = 0; q < NREP; ++q) y[q] = ldcg_c(reinterpret_cast<const cplx*>(a.acc_yv) + q * PW + ip);
+        const cplx ypiv = (i < pw) ? ldcg_c(&Yp[(long)ip * a.ldp + c]) : mk(0, 0);
+#pragma unroll
+        for (int q = 1; q < NREP; ++q) y[0] = cadd(y[0], y[q]);
+        s_yv = y[0];
+        s_ypiv = ypiv;
       }
       __syncthreads();
       PT_MARK(0);
@@ -277,7 +268,6 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       break;
     }
     PT_MARK(1);
-    double nrm = 0.0;
     {
       const int ip = i - 1;
       const cplx taup = s_tau_prev, alphap = s_alpha_prev;
@@ -315,17 +305,11 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
             av = csub(av, acc2);
             a.A[(long)c * a.lda + r] = av;
           }
-          if (r >= c + 2) nrm += cabs2(av);
           if (chunks > 1) Yp[(long)i * a.ldp + r] = mk(0, 0);  // the chunks add their partial y in phase B
         }
       }
     }
     PT_MARK(2);
-    {
-      double v1[1] = {nrm};
-      block_sum<1>(v1, sblk);
-      if (tid == 0) a.pnorm[blockIdx.x] = v1[0];
-    }
     PT_MARK(3);
     grid_bar(a.bar, ++epoch);
     PT_MARK(4);
@@ -346,23 +330,21 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       }
     }
     const cplx alpha = ldcg_c(&a.A[(long)c * a.lda + c + 1]);
-    if (tid >= NT - 32) {  // |x|^2 from the per-CTA partials
-      const int lane = tid - (NT - 32);
-      double x = 0.0;
-      for (int g = lane; g < (int)gridDim.x; g += 32) x += __ldcg(&a.pnorm[g]);
-      x = warp_sum(x);
-      if (lane == 0) s_xn2 = x;
-    }
+    double nloc;
     {
       // scalars and the raw column are fetched in one round of independent loads; scaling happens in shared memory
       const cplx* colp = a.A + (long)c * a.lda + c + 1;
       int j = tid;
+      nloc = 0.0;
       for (; j + 7 * NT < nv; j += 8 * NT) {
         cplx x[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) x[u] = ldcg_c(colp + j + u * NT);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sv[j + u * NT] = x[u];
+        for (int u = 0; u < 8; ++u) {
+          sv[j + u * NT] = x[u];
+          if (j + u * NT > 0) nloc += cabs2(x[u]);
+        }
       }
       for (; j + 3 * NT < nv; j += 4 * NT) {
         const cplx x0 = ldcg_c(colp + j), x1 = ldcg_c(colp + j + NT), x2 = ldcg_c(colp + j + 2 * NT),
@@ -371,12 +353,23 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
         sv[j + NT] = x1;
         sv[j + 2 * NT] = x2;
         sv[j + 3 * NT] = x3;
+        nloc += ((j > 0) ? cabs2(x0) : 0.0) + cabs2(x1) + cabs2(x2) + cabs2(x3);
       }
-      for (; j < nv; j += NT) sv[j] = ldcg_c(colp + j);
+      for (; j < nv; j += NT) {
+        const cplx x0 = ldcg_c(colp + j);
+        sv[j] = x0;
+        if (j > 0) nloc += cabs2(x0);
+      }
     }
+    // |x|^2 (below the pivot element): every CTA holds the whole column, so the norm needs no grid-wide reduction;
+    // all CTAs add the same numbers in the same order and get bit-identical reflectors
+    nloc = warp_sum(nloc);
+    if ((tid & 31) == 0) sblk[tid >> 5] = nloc;
     __syncthreads();
     PT_MARK(5);
-    const double xn2 = s_xn2;
+    double xn2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) xn2 += sblk[w];
     double beta;
     cplx tau, scal;
     if (xn2 == 0.0 && alpha.y == 0.0) {
@@ -526,10 +519,17 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
       }
     }
     PT_MARK(8);
-    {
-      double v2[2] = {yv0, yv1};
-      block_sum<2>(v2, sblk);
-      if (tid == 0) reinterpret_cast<double2*>(a.pyv)[blockIdx.x] = make_double2(v2[0], v2[1]);
+    if (tid < 32) {  // y^H v: the partial sums live in the cl == 0 threads (lanes 0..15 of warp 0)
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        yv0 += __shfl_xor_sync(0xffffffffu, yv0, o);
+        yv1 += __shfl_xor_sync(0xffffffffu, yv1, o);
+      }
+      if (tid == 0 && (yv0 != 0.0 || yv1 != 0.0)) {
+        double* yp = a.acc_yv + 2 * ((blockIdx.x % NREP) * PW + i);
+        atomicAdd(yp, yv0);
+        atomicAdd(yp + 1, yv1);
+      }
     }
     PT_MARK(9);
     grid_bar(a.bar, ++epoch);
@@ -641,8 +641,8 @@ void Heig::init() {
   int dev = 0;
   TEVO_CUDA_CHECK(cudaGetDevice(&dev));
   TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
-  // [pnorm MAXCTA | pyv 2*MAXCTA | barrier counter (one 128-byte line) | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
-  TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (3 * MAXCTA + 16 + 2 * NREP * 2 * PW * PW)));
+  // [barrier counter (one 128-byte line) | acc_yv NREP*2*PW | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
+  TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW)));
 }
 
 void Heig::destroy() {
@@ -695,8 +695,8 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
                                          (int)(2 * sizeof(cplx) * TRB * TRB)));
   });
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
-  double* zero_from = acc_ + 3 * MAXCTA;  // flags and the replicated accumulators are cleared before every panel
-  const size_t zero_bytes = sizeof(double) * (16 + 2 * NREP * 2 * PW * PW);
+  double* zero_from = acc_;  // the barrier counter and the replicated accumulators are cleared before every panel
+  const size_t zero_bytes = sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
   TEVO_CUDA_CHECK(cudaMemsetAsync(Sall_, 0, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW), st));
   int p0 = 0;
@@ -705,9 +705,9 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     TEVO_CUDA_CHECK(cudaMemsetAsync(zero_from, 0, zero_bytes, st));
     PanelArgs pa;
     pa.n = n; pa.p0 = p0; pa.pw = pw; pa.A = A; pa.lda = lda; pa.P = P_; pa.Q = Q_; pa.Y = Y_; pa.ldp = n;
-    pa.pnorm = acc_; pa.pyv = acc_ + MAXCTA;
     pa.bar = reinterpret_cast<unsigned*>(zero_from);
-    pa.acc_cw = zero_from + 16;
+    pa.acc_yv = zero_from + 16;
+    pa.acc_cw = pa.acc_yv + NREP * 2 * PW;
     pa.acc_cv = pa.acc_cw + NREP * 2 * PW * PW;
     pa.cv_out = Sall_ + (size_t)(p0 / PW) * 2 * PW * PW;
     pa.d = d_; pa.e = e_; pa.taus = taus_;
