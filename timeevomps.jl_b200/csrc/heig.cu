@@ -239,13 +239,13 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
           if (i < pw) pivW[ip] = cadd(cmul(tau_cur, csub(s_ypiv, acc)), cmul(alphap, pivV[ip]));
         }
       }
-      __syncthreads();
+      // no barrier here: the scalars are consumed only behind the barriers of the row reductions below, so the other
+      // warps start their panel products while warp 0 finishes the scalar chain
     }
     if (i == pw) {
       // last pass: only finalise w_{pw-1} on the own rows, then leave the column loop
       const int ip = pw - 1;
       const int cp = p0 + ip;
-      const cplx taup = s_tau_prev, alphap = s_alpha_prev;
       int sidx = 0;
       for (int s = own_first; s < nstrips; s += s_step, ++sidx) {
         const int r = p0 + s * RS + rr;
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
           const cplx y = (chunks > 1) ? ldcg_c(&Yp[(long)ip * a.ldp + r])
                                       : (sidx < smax ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r]);
           const cplx v = ldV(sidx, ip, r);
-          Wp[(long)ip * a.ldp + r] = cadd(cmul(taup, csub(y, tot)), cmul(alphap, v));
+          Wp[(long)ip * a.ldp + r] = cadd(cmul(s_tau_prev, csub(y, tot)), cmul(s_alpha_prev, v));
         }
       }
       break;
@@ -270,12 +270,13 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     PT_MARK(1);
     {
       const int ip = i - 1;
-      const cplx taup = s_tau_prev, alphap = s_alpha_prev;
       int sidx = 0;
       for (int s = own_first; s < nstrips; s += s_step, ++sidx) {
         const int r = p0 + s * RS + rr;
         const bool act = (r < n) && (r >= c);
         cplx acc1 = mk(0, 0), acc2 = mk(0, 0);
+        cplx ypre = mk(0, 0);  // partial y combined by the chunks: one L2 round trip, overlapped with the products
+        if (chunks > 1 && cl == 0 && act && i > 0) ypre = ldcg_c(&Yp[(long)ip * a.ldp + r]);
         if (act && i > 0) {
 #pragma unroll 4
           for (int k = cl; k < ip; k += 16) {
@@ -294,10 +295,9 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
           // inside this launch before this point)
           cplx av = (res && i > 0) ? sres[sidx * SB + 2 * PW * RS + RS + rr] : a.A[(long)c * a.lda + r];
           if (i > 0) {
-            const cplx y = (chunks > 1) ? ldcg_c(&Yp[(long)ip * a.ldp + r])
-                                        : (res ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r]);
+            const cplx y = (chunks > 1) ? ypre : (res ? sres[sidx * SB + 2 * PW * RS + rr] : Yp[(long)ip * a.ldp + r]);
             const cplx v = ldV(sidx, ip, r);
-            const cplx wf = cadd(cmul(taup, csub(y, acc1)), cmul(alphap, v));
+            const cplx wf = cadd(cmul(s_tau_prev, csub(y, acc1)), cmul(s_alpha_prev, v));
             Wp[(long)ip * a.ldp + r] = wf;
             if (res) sres[sidx * SB + (PW + ip) * RS + rr] = wf;
             cfma(acc2, v, cconj(pivW[ip]));
@@ -372,16 +372,25 @@ __global__ void __launch_bounds__(NT, 1) tridiag_panel_kernel(PanelArgs a) {
     for (int w = 0; w < NT / 32; ++w) xn2 += sblk[w];
     double beta;
     cplx tau, scal;
-    if (xn2 == 0.0 && alpha.y == 0.0) {
+    const double s2 = cabs2(alpha) + xn2;
+    if ((xn2 == 0.0 && alpha.y == 0.0) || !(s2 > 1e-290)) {  // nothing to annihilate (or a column of underflows)
       beta = alpha.x;
       tau = mk(0, 0);
       scal = mk(0, 0);
     } else {
-      beta = -copysign(sqrt(cabs2(alpha) + xn2), alpha.x);
-      tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+      // |x| and 1/|x| from one reciprocal square root (+ a Newton correction), 1/(alpha - beta) from one
+      // reciprocal: the sqrt -> divide chain is on the critical path of every column
+      double rs = rsqrt(s2);
+      double nx = s2 * rs;
+      nx = fma(0.5 * rs, fma(-nx, nx, s2), nx);
+      rs = fma(rs, fma(-nx, rs, 1.0), rs);
+      beta = -copysign(nx, alpha.x);
+      const double ib = -copysign(rs, alpha.x);
+      tau = mk((beta - alpha.x) * ib, -alpha.y * ib);
       const cplx den = mk(alpha.x - beta, alpha.y);
       const double dn = cabs2(den);
-      scal = mk(den.x / dn, -den.y / dn);
+      double rdn = __drcp_rn(dn);
+      scal = mk(den.x * rdn, -den.y * rdn);
     }
     tau_cur = tau;
     if (blockIdx.x == 0 && tid == 0) {
