@@ -197,6 +197,10 @@ int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* theta, cons
 /* Hermitian eigen-decomposition of a host n x n matrix (full storage, column-major): eigenvalues in descending
  * order and the matching eigenvectors (columns of U) - the core of the split, exposed for tests */
 int tevo_test_heig(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U);
+/* same with the tridiagonalisation kernel limited to max_ctas CTAs (0 = all SMs): the configuration the lanes of the
+ * layer-parallel mode run in (several 16-row strips per CTA) */
+int tevo_test_heig_ctas(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U,
+                        int max_ctas);
 
 /* per-phase device timing with CUDA events on the library stream (bench.py's roofline object).  Off by default. */
 int tevo_profile_enable(int on);

@@ -149,6 +149,29 @@ def test_heig_random_hermitian(tevo, n):
     assert np.abs(A @ U - U * w).max() <= 1e-13 * nrm * max(1, n)
 
 
+@pytest.mark.parametrize("n,ctas", [(300, 7), (300, 3), (520, 5), (333, 1), (200, 40)])
+def test_heig_capped_grid(tevo, n, ctas):
+    """The panel kernel with fewer CTAs than 16-row strips (several strips per CTA, some beyond the shared-memory
+    resident ones): the configuration of the lanes in the layer-parallel mode."""
+    from timeevomps_jl_b200._lib import load, check, default_ctx
+    ctx = default_ctx()
+    rng = np.random.default_rng(1000 * n + ctas)
+    X = _rand(rng, n, n)
+    A = np.asfortranarray(X + X.conj().T)
+    w = np.zeros(n)
+    U = np.zeros((n, n), dtype=np.complex128, order="F")
+    check(load().tevo_test_heig_ctas(ctx.h, n, A.ctypes.data, w.ctypes.data_as(C.POINTER(C.c_double)), U.ctypes.data,
+                                     ctas), ctx.h)
+    wr = np.linalg.eigvalsh(A)[::-1]
+    nrm = np.abs(wr).max()
+    assert np.abs(w - wr).max() <= 1e-13 * nrm * n ** 0.5
+    assert np.abs(U.conj().T @ U - np.eye(n)).max() <= 1e-13 * n ** 0.5
+    assert np.abs(A @ U - U * w).max() <= 1e-13 * nrm * n
+    # and the default grid still gives the same spectrum afterwards (the cap is restored)
+    w2, _ = _heig(tevo, A)
+    assert np.abs(w2 - wr).max() <= 1e-13 * nrm * n ** 0.5
+
+
 @pytest.mark.parametrize("kind", ["lowrank", "graded", "clustered", "zero", "identity"])
 def test_heig_hard_spectra(tevo, kind):
     rng = np.random.default_rng(11)

@@ -90,6 +90,7 @@ PROTOTYPES = {
     "tevo_test_split": (_I, [_P, _I, _I, _CP, C.POINTER(tevo_trunc), _I, _I, C.POINTER(tevo_spec), _DP, _I, _CP, _CP,
                              _I]),
     "tevo_test_heig": (_I, [_P, _I, _CP, _DP, _CP]),
+    "tevo_test_heig_ctas": (_I, [_P, _I, _CP, _DP, _CP, _I]),
     "tevo_mps_to_bform": (_I, [_P]),
     "tevo_apply_layer_bform": (_I, [_P, _I, _IP, _CP, C.POINTER(tevo_trunc), _I, C.POINTER(tevo_spec), _DP, _I]),
     "tevo_bform_expect_site": (_I, [_P, _I, _I, _CP, _CP]),

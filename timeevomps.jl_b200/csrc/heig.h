@@ -15,6 +15,7 @@ class Heig {
   const double* evals() const { return evals_; }
   // cap on the CTAs of the panel kernel (two lanes share the SMs in the layer-parallel mode); 0 = all SMs
   void set_max_ctas(int n) { max_ctas_ = n; }
+  int max_ctas() const { return max_ctas_; }
   // U(:, i) = eigenvector of column perm[i] (indices into the ascending order), i < k.  U is n x k, ld = ldu.
   void vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ldu);
 

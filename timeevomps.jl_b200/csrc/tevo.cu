@@ -1380,6 +1380,17 @@ extern "C" int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* 
   TEVO_CATCH
 }
 
+extern "C" int tevo_test_heig_ctas(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U,
+                                   int max_ctas) {
+  if (!ctx || max_ctas < 0) return TEVO_EINVAL;
+  tevo::Heig& h = ctx->split.heig();
+  const int saved = h.max_ctas();
+  h.set_max_ctas(max_ctas);
+  const int rc = tevo_test_heig(ctx, n, A, evals_desc, U);
+  h.set_max_ctas(saved);
+  return rc;
+}
+
 extern "C" int tevo_test_heig(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U) {
   TEVO_TRY(ctx)
   require(ctx && A && evals_desc && U && n >= 1, "tevo_test_heig: bad argument");
