@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-sample-gates", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu-1thread", action="store_true", help="skip the single-thread CPU baseline sample")
     ap.add_argument("--mode", default="auto", choices=["auto", "sequential", "parallel"],
                     help="sequential: the reference's algorithm (centre moves between gates; default at 1 GPU); "
                          "parallel: layer-parallel (Hastings) TEBD, chain-segment sharded over the ranks with NCCL "
@@ -159,6 +160,20 @@ class CpuArm:
                 "sample": "%d interior two-site updates (QR centre move + theta + gate + LAPACK SVD split) at chi=%d on "
                           "a %d-site window, %.2f s/update, extrapolated x%d updates per TEBD4 step"
                           % (ngates, chi, self.nw, per_gate, gates_per_step(self.args.nsites))}
+
+
+def _cpu_arm_one_thread(self):
+    """One more interior update with the BLAS pool limited to a single thread (bounded: one update)."""
+    try:
+        import threadpoolctl
+    except Exception:
+        return {"value_1thread": None, "sample_1thread": "threadpoolctl not available"}
+    with threadpoolctl.threadpool_limits(limits=1):
+        one = self.sample(1)
+    return {"value_1thread": one["value"], "sample_1thread": "1 interior update, BLAS limited to 1 thread"}
+
+
+CpuArm.sample_one_thread = _cpu_arm_one_thread
 
 
 def workload_string(args):
@@ -577,7 +592,11 @@ def main():
     except Exception:
         pass
     if not args.no_cpu:
-        line["cpu_baseline"] = CpuArm(args).sample(args.cpu_sample_gates)
+        arm = CpuArm(args)
+        line["cpu_baseline"] = arm.sample(args.cpu_sample_gates)
+        if not args.no_cpu_1thread:
+            # the baseline is stated for all BLAS threads (value, cores) and for one thread
+            line["cpu_baseline"].update(arm.sample_one_thread())
     print(json.dumps(line))
 
 
