@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "kernels.h"
@@ -48,6 +49,98 @@ __global__ void __launch_bounds__(1024) potrf_block_kernel(int nb, const cplx* _
     Xm[(long)p * ld + r] = (r >= p) ? cscale(sinv[r], x[p][r]) : mk(0, 0);
   }
   if (tid == 0) {
+    stats[0] = pmin;
+    stats[1] = pmax;
+  }
+}
+
+// Register-tiled version of the same factorisation (default): 256 threads, thread (ti, tj) keeps the 4 x 4 tiles
+// A(4ti.., 4tj..) and inv(L)(4ti.., 4tj..) in registers; per column k only the column of A and the row of inv(L) go
+// through (double-buffered) shared memory, one barrier per column.  Same deferred pivot scaling as
+// chol_inv_lower_smem: the updates divide by the pivot, L(i,k) = a(i,k)/l_k and inv(L)(i,c) = x(i,c)/l_i are applied
+// when the results are written.  The 1024-thread shared-memory version spends ~90 us per block on index arithmetic
+// (issue-bound); this one does 32 complex FMAs per 12 shared-memory loads.
+__global__ void __launch_bounds__(256) potrf_block_reg_kernel(int nb, const cplx* __restrict__ G, cplx* __restrict__ Lm,
+                                                              cplx* __restrict__ Xm, long ld,
+                                                              double* __restrict__ stats) {
+  __shared__ cplx scol[2][NB];  // column k of A (unscaled), rows 0..63
+  __shared__ cplx srow[2][NB];  // row k of inv(L) (unscaled), columns 0..63
+  __shared__ double sinv[NB];
+  const int t = threadIdx.x, ti = t / 16, tj = t % 16;
+  cplx a[4][4], x[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * ti + r, j = 4 * tj + c;
+      a[r][c] = (i < nb && j < nb) ? (i >= j ? G[(long)j * ld + i] : mk(0, 0)) : mk(i == j ? 1.0 : 0.0, 0.0);
+      x[r][c] = mk((i == j && i < nb) ? 1.0 : 0.0, 0.0);
+    }
+  double pmin = 1e300, pmax = 0.0;
+  for (int kb = 0; kb < NB / 4; ++kb) {
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+      const int k = 4 * kb + kc;
+      if (k >= nb) continue;  // uniform
+      const int buf = k & 1;
+      if (tj == kb) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) scol[buf][4 * ti + r] = a[r][kc];
+      }
+      if (ti == kb) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) srow[buf][4 * tj + c] = x[kc][c];
+      }
+      __syncthreads();
+      const double dkk = scol[buf][k].x;
+      if (!(dkk > 0.0) || !isfinite(dkk)) {  // uniform: every thread reads the same pivot
+        if (t == 0) {
+          stats[0] = -1.0;
+          stats[1] = 0.0;
+        }
+        return;
+      }
+      const double inv = rsqrt(dkk), l = dkk * inv, rd = inv * inv;
+      pmin = fmin(pmin, l);
+      pmax = fmax(pmax, l);
+      if (t == 0) sinv[k] = inv;
+      if (ti >= kb) {
+        cplx li[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) li[r] = (4 * ti + r > k) ? cscale(rd, scol[buf][4 * ti + r]) : mk(0, 0);
+        if (tj >= kb) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const cplx lj = (4 * tj + c > k) ? cconj(scol[buf][4 * tj + c]) : mk(0, 0);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r][c] = csub(a[r][c], cmul(li[r], lj));
+          }
+        }
+        if (tj <= kb) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const cplx xr = srow[buf][4 * tj + c];  // zero for columns > k
+#pragma unroll
+            for (int r = 0; r < 4; ++r) x[r][c] = csub(x[r][c], cmul(li[r], xr));
+          }
+        }
+      }
+      // no second barrier: column k+1 uses the other buffer, and its barrier orders the writes of column k+2 after
+      // these reads
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = 4 * ti + r, j = 4 * tj + c;
+      if (i < nb && j < nb) {
+        Lm[(long)j * ld + i] = (i > j) ? cscale(sinv[j], a[r][c]) : (i == j ? mk(a[r][c].x * sinv[j], 0.0) : mk(0, 0));
+        Xm[(long)j * ld + i] = (i >= j) ? cscale(sinv[i], x[r][c]) : mk(0, 0);
+      }
+    }
+  if (t == 0) {
     stats[0] = pmin;
     stats[1] = pmax;
   }
@@ -141,8 +234,13 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   ProfScope* pf = new ProfScope(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
-    potrf_block_kernel<<<1, 1024, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
-                                         d_stats_ + 2 * jb);
+    static const bool smem_version = getenv("TEVO_POTRF_SMEM") != nullptr;  // the 1024-thread shared-memory kernel
+    if (smem_version)
+      potrf_block_kernel<<<1, 1024, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j,
+                                                                       X + (long)j * n + j, n, d_stats_ + 2 * jb);
+    else
+      potrf_block_reg_kernel<<<1, 256, 0, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
+                                                d_stats_ + 2 * jb);
     TEVO_LAUNCHED();
     if (rest > 0) {
       // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H ; trailing: G(j+nb:, j+nb:) -= panel * panel^H

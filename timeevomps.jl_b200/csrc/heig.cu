@@ -660,6 +660,8 @@ void Heig::destroy() {
     if (p) cudaFree(p);
   };
   fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(acc_); fr(Tblk_); fr(X_); fr(part_);
+  fr(pair_);
+  pair_ = nullptr;
   Y_ = nullptr;
   P_ = Q_ = VT_ = nullptr;
   Sall_ = nullptr;
@@ -673,7 +675,7 @@ void Heig::ensure(int n) {
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
-  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_); fr(Tblk_);
+  fr(P_); fr(Q_); fr(Y_); fr(Sall_); fr(VT_); fr(d_); fr(e_); fr(taus_); fr(evals_); fr(Z_); fr(X_); fr(Tblk_); fr(pair_);
   const size_t nn = (size_t)n * n;
   TEVO_CUDA_CHECK(cudaMalloc(&Tblk_, sizeof(cplx) * PW * PW * (size_t)((n + PW - 1) / PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&P_, sizeof(cplx) * (size_t)n * 2 * PW));
@@ -686,7 +688,8 @@ void Heig::ensure(int n) {
   TEVO_CUDA_CHECK(cudaMalloc(&taus_, sizeof(cplx) * ((size_t)n + PW)));
   TEVO_CUDA_CHECK(cudaMalloc(&evals_, sizeof(double) * n));
   TEVO_CUDA_CHECK(cudaMalloc(&Z_, sizeof(double) * nn));
-  TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)2 * PW * n));
+  TEVO_CUDA_CHECK(cudaMalloc(&pair_, sizeof(cplx) * 3 * PW * PW * (size_t)(n / (2 * PW) + 1)));
   xcap_ = n;
   cap_ = n;
 }
@@ -785,6 +788,22 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
       zgemm(st, OP_N, OP_N, n, n - q0, n - q0, ONE, A + (long)q0 * lda, lda, Tblk_ + (long)nfull * PW * PW, PW, ZERO,
             VT_ + (long)q0 * n, n);
     }
+    // pairs of adjacent full-width panels become one 128-wide block reflector for the back-transformation:
+    //   H_a H_b = I - [V_a V_b] [[T_a, T_ab], [0, T_b]] [V_a V_b]^H,   T_ab = -T_a (V_a^H V_b) T_b,
+    // so (V T)_b gains V_a T_ab.  (A 64-row operand fills only half of the 128-row GEMM tile.)
+    static const bool no_pairs = getenv("TEVO_BACK64") != nullptr;
+    npairs_ = no_pairs ? 0 : nfull / 2;
+    if (npairs_ > 0) {
+      const long bsA = 2L * PW * lda, bsT = 2L * PW * PW, bsP = (long)PW * PW;
+      cplx* S12 = pair_;
+      cplx* W1 = pair_ + (size_t)npairs_ * PW * PW;
+      cplx* T12 = pair_ + (size_t)2 * npairs_ * PW * PW;
+      zgemm_batched(st, OP_C, OP_N, PW, PW, n, ONE, A, lda, bsA, A + (long)PW * lda, lda, bsA, ZERO, S12, PW, bsP, npairs_);
+      zgemm_batched(st, OP_N, OP_N, PW, PW, PW, ONE, Tblk_, PW, bsT, S12, PW, bsP, ZERO, W1, PW, bsP, npairs_);
+      zgemm_batched(st, OP_N, OP_N, PW, PW, PW, MONE, W1, PW, bsP, Tblk_ + bsP, PW, bsT, ZERO, T12, PW, bsP, npairs_);
+      zgemm_batched(st, OP_N, OP_N, n, PW, PW, ONE, A, lda, bsA, T12, PW, bsP, ONE, VT_ + (long)PW * n, n, 2L * PW * n,
+                    npairs_);
+    }
   }
   {
     ProfScope ps(st, P_STEDC);
@@ -807,17 +826,24 @@ void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ld
   if ((size_t)k > xcap_) {
     if (X_) cudaFree(X_);
     X_ = nullptr;
-    TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)PW * k));
+    TEVO_CUDA_CHECK(cudaMalloc(&X_, sizeof(cplx) * (size_t)2 * PW * k));
     xcap_ = k;
   }
-  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= (V T) (V^H U)
+  // U = H_0 ... H_{n-2} Z : apply the panels last to first,  U -= (V T) (V^H U); the panels below 2*npairs_ go in
+  // pairs (128 columns of V and V T at a time), the ones above singly
   int last = ((n - 2) / PW) * PW;
-  for (int p0 = last; p0 >= 0; p0 -= PW) {
+  for (int p0 = last; p0 >= 2 * npairs_ * PW; p0 -= PW) {
     const int pw = std::min(PW, n - 1 - p0);
     const int rows = n - p0;
     zgemm_splitk(st, OP_C, OP_N, pw, k, rows, ONE, A_ + (long)p0 * lda_ + p0, lda_, U + p0, ldu, ZERO, X_, PW, &part_,
                  &part_cap_);
     zgemm(st, OP_N, OP_N, rows, k, pw, MONE, VT_ + (long)p0 * n + p0, n, X_, PW, ONE, U + p0, ldu);
+  }
+  for (int q = npairs_ - 1; q >= 0; --q) {
+    const int p0 = 2 * q * PW, rows = n - p0;
+    zgemm_splitk(st, OP_C, OP_N, 2 * PW, k, rows, ONE, A_ + (long)p0 * lda_ + p0, lda_, U + p0, ldu, ZERO, X_, 2 * PW,
+                 &part_, &part_cap_);
+    zgemm(st, OP_N, OP_N, rows, k, 2 * PW, MONE, VT_ + (long)p0 * n + p0, n, X_, 2 * PW, ONE, U + p0, ldu);
   }
 }
 

@@ -28,6 +28,8 @@ class Heig {
   cplx* A_ = nullptr;
   long lda_ = 0;
   cplx *P_ = nullptr, *Q_ = nullptr, *Y_ = nullptr, *VT_ = nullptr, *taus_ = nullptr, *Tblk_ = nullptr, *X_ = nullptr, *part_ = nullptr;
+  cplx* pair_ = nullptr;  // per pair of panels: V1^H V2, T1 V1^H V2, T12 (64 x 64 each)
+  int npairs_ = 0;        // pairs of adjacent full-width panels applied as one 128-wide block reflector
   size_t xcap_ = 0, part_cap_ = 0;
   double *Sall_ = nullptr, *d_ = nullptr, *e_ = nullptr, *evals_ = nullptr, *Z_ = nullptr, *acc_ = nullptr;
 };
