@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--cpu-sample-gates", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-cpu-1thread", action="store_true", help="skip the single-thread CPU baseline sample")
+    ap.add_argument("--cpu-1thread", action="store_true",
+                    help="also time one update with the BLAS pool limited to one thread (adds ~1 min at chi=1024)")
     ap.add_argument("--mode", default="auto", choices=["auto", "sequential", "parallel"],
                     help="sequential: the reference's algorithm (centre moves between gates; default at 1 GPU); "
                          "parallel: layer-parallel (Hastings) TEBD, chain-segment sharded over the ranks with NCCL "
@@ -594,7 +595,7 @@ def main():
     if not args.no_cpu:
         arm = CpuArm(args)
         line["cpu_baseline"] = arm.sample(args.cpu_sample_gates)
-        if not args.no_cpu_1thread:
+        if args.cpu_1thread:
             # the baseline is stated for all BLAS threads (value, cores) and for one thread
             line["cpu_baseline"].update(arm.sample_one_thread())
     print(json.dumps(line))
