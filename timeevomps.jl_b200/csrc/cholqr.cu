@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <optional>
 #include <vector>
 
 #include "kernels.h"
@@ -231,7 +232,8 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
     ProfScope ps(st, P_CHOL_GRAM);
     zgemm_herm(st, OP_C, OP_N, n, m, ONE, A, m, A, m, ZERO, G_, n, false);  // Cholesky reads the lower part only
   }
-  ProfScope* pf = new ProfScope(st, P_CHOL_FACTOR);
+  std::optional<ProfScope> pf;
+  pf.emplace(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
     static const bool smem_version = getenv("TEVO_POTRF_SMEM") != nullptr;  // the 1024-thread shared-memory kernel
@@ -250,8 +252,9 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
                  G_ + (long)(j + nb) * n + j + nb, n, false);
     }
   }
-  delete pf;
-  ProfScope* pi = new ProfScope(st, P_CHOL_INV);
+  pf.reset();
+  std::optional<ProfScope> pi;
+  pi.emplace(st, P_CHOL_INV);
   // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
   // regular part: n = q * NB (+ tail); level s merges blocks [lo, lo+s) and [lo+s, lo+2s), all pairs of a level in
   // two strided-batched GEMMs.  Irregular leftovers (n not a multiple of 2s) are merged one by one afterwards.
@@ -285,7 +288,7 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
     for (; k < bounds.size(); ++k) nbnd.push_back(bounds[k]);
     bounds = nbnd;
   }
-  delete pi;
+  pi.reset();
   // Q = A * inv(L)^H
   ProfScope pq(st, P_CHOL_Q);
   zgemm(st, OP_N, OP_C, m, n, n, ONE, A, m, X, n, ZERO, Q, m);
