@@ -711,8 +711,21 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   const size_t zero_bytes = sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
   TEVO_CUDA_CHECK(cudaMemsetAsync(Sall_, 0, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW), st));
+  // experimental: hand the last columns to the cluster-resident kernel (tail.cu) once the trailing matrix fits it
+  static const int tail_cluster = [] {
+    const char* e = getenv("TEVO_CLUSTER_TAIL");
+    return e ? atoi(e) : 0;
+  }();
+  static const int tail_max = tail_cluster > 0 ? tridiag_tail_max_m(tail_cluster) : 0;
+  int tail_t0 = -1;
   int p0 = 0;
   while (p0 < n - 1) {
+    if (tail_max > 0 && n - p0 <= tail_max && n - p0 >= 2) {
+      ProfScope ps(st, P_TRI_PANEL);
+      tridiag_tail(st, tail_cluster, n, p0, A, lda, d_, e_, taus_);
+      tail_t0 = p0;
+      break;
+    }
     const int pw = std::min(PW, n - 1 - p0);
     TEVO_CUDA_CHECK(cudaMemsetAsync(zero_from, 0, zero_bytes, st));
     PanelArgs pa;
@@ -772,6 +785,19 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   }
   last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
   TEVO_LAUNCHED();
+  if (tail_t0 >= 0) {
+    // the tail kernel keeps no panel dots: V^H V of its panels (the input of the compact-WY factors) by GEMM
+    const cplx ONE1 = mk(1, 0), ZERO1 = mk(0, 0);
+    cplx* S = reinterpret_cast<cplx*>(Sall_) + (size_t)(tail_t0 / PW) * PW * PW;
+    const cplx* Vt = A + (long)tail_t0 * lda;
+    const int nfull_tail = (n - tail_t0) / PW, wlast = (n - tail_t0) % PW;
+    if (nfull_tail > 0)
+      zgemm_batched(st, OP_C, OP_N, PW, PW, n, ONE1, Vt, lda, (long)PW * lda, Vt, lda, (long)PW * lda, ZERO1, S, PW,
+                    (long)PW * PW, nfull_tail);
+    if (wlast > 0)
+      zgemm(st, OP_C, OP_N, wlast, wlast, n, ONE1, Vt + (long)nfull_tail * PW * lda, lda, Vt + (long)nfull_tail * PW * lda,
+            lda, ZERO1, S + (size_t)nfull_tail * PW * PW, PW);
+  }
   if (n > 1) {
     // compact-WY factors of all panels in one launch, then V*T for the back-transformation as one batched GEMM over
     // the full-width panels (A holds V with explicit zeros above the reflectors) plus one for a narrower last panel

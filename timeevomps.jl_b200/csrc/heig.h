@@ -5,6 +5,10 @@
 
 namespace tevo {
 
+// experimental cluster-resident tail of the tridiagonalisation (tail.cu; enabled by TEVO_CLUSTER_TAIL=<cluster size>)
+int tridiag_tail_max_m(int cluster);
+void tridiag_tail(cudaStream_t st, int cluster, int n, int t0, cplx* A, long lda, double* d, double* e, cplx* taus);
+
 class Heig {
  public:
   void init();
