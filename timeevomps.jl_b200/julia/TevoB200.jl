@@ -187,6 +187,89 @@ function measure_bond(dpsi::DeviceMPS, b::Int, ops::Vector{Matrix{ComplexF64}})
     return reshape(out, 2, length(ops))
 end
 
+# ---- state maintenance and observables on the device ---------------------------------------------------
+"orthogonalize!(psi, j) (src/bondgate.jl:48, src/tdvp.jl:51)."
+orthogonalize!(dpsi::DeviceMPS, j::Int) =
+    check(dpsi.ctx, ccall((:tevo_mps_orthogonalize, LIB), Cint, (Ptr{Cvoid}, Cint), dpsi.h, j - 1))
+
+"reorthogonalize!(psi) (src/itensor.jl:28-33, called at src/tebd.jl:174)."
+reorthogonalize!(dpsi::DeviceMPS) = check(dpsi.ctx, ccall((:tevo_mps_reorthogonalize, LIB), Cint, (Ptr{Cvoid},), dpsi.h))
+
+"psi[i] /= norm(psi[i]) (src/tdvp.jl:84-87)."
+normalize_site!(dpsi::DeviceMPS, i::Int) =
+    check(dpsi.ctx, ccall((:tevo_mps_normalize_site, LIB), Cint, (Ptr{Cvoid}, Cint), dpsi.h, i - 1))
+
+"deepcopy(psi) on the device."
+function Base.copy(dpsi::DeviceMPS)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(dpsi.ctx, ccall((:tevo_mps_copy, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), dpsi.h, r))
+    c = DeviceMPS(dpsi.ctx, r[], dpsi.sites, dpsi.linktags)
+    finalizer(x -> ccall((:tevo_mps_free, LIB), Cint, (Ptr{Cvoid},), x.h), c)
+    return c
+end
+
+"inner(a, b) = <a|b> (test/test_tebd.jl:16,28,46)."
+function inner(a::DeviceMPS, b::DeviceMPS)
+    out = Ref{ComplexF64}(0)
+    check(a.ctx, ccall((:tevo_mps_inner, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{ComplexF64}), a.h, b.h, out))
+    return out[]
+end
+
+"measure!(psi, op, j) (src/testutils.jl:55-58): moves the centre to j and returns <O_j>; O[s',s] as a d x d matrix."
+function expect(dpsi::DeviceMPS, O::Matrix{ComplexF64}, j::Int)
+    flat = vec(permutedims(O))                                   # row-major
+    out = Ref{ComplexF64}(0)
+    GC.@preserve flat check(dpsi.ctx, ccall((:tevo_mps_expect_site, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ref{ComplexF64}), dpsi.h, j - 1, flat, out))
+    return out[]
+end
+
+"One term of measure(H::GateList, psi) (src/bondgate.jl:71-79): <h_b> for the bond operator h (d^2 x d^2, as gate_matrix)."
+function gate_expect(dpsi::DeviceMPS, h::ITensor, b::Int)
+    g = gate_matrix(h, dpsi.sites[b], dpsi.sites[b + 1])
+    out = Ref{ComplexF64}(0)
+    GC.@preserve g check(dpsi.ctx, ccall((:tevo_gate_expect, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ref{ComplexF64}), dpsi.h, b - 1, g, out))
+    return out[]
+end
+
+# ---- layer-parallel mode (NOT the reference's algorithm, see DESIGN.md section 8) ------------------------
+"Bring the state to the canonical B form with Schmidt values on every bond; the gates of a layer become independent."
+to_bform!(dpsi::DeviceMPS) = check(dpsi.ctx, ccall((:tevo_mps_to_bform, LIB), Cint, (Ptr{Cvoid},), dpsi.h))
+
+"All gates of one even/odd layer at once (Hastings' update); same arguments as apply_gates! without `reversed`."
+function apply_gates_parallel!(dpsi::DeviceMPS, Gs::Vector{<:Tuple{ITensor,Int}}; normalize=true, kwargs...)
+    n = length(Gs)
+    bonds = Cint[b - 1 for (_, b) in Gs]
+    gs = reduce(vcat, [gate_matrix(G, dpsi.sites[b], dpsi.sites[b + 1]) for (G, b) in Gs])
+    tr = Ref(trunc_from(; kwargs...))
+    specs = Vector{TevoSpec}(undef, n)
+    GC.@preserve bonds gs specs check(dpsi.ctx, ccall((:tevo_apply_layer_bform, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{ComplexF64}, Ref{TevoTrunc}, Cint, Ptr{TevoSpec}, Ptr{Cdouble}, Cint),
+        dpsi.h, n, bonds, gs, tr, normalize ? 1 : 0, specs, C_NULL, 0))
+    return specs
+end
+
+"<O_j> for several one-site operators in the B form (no centre move)."
+function bform_expect(dpsi::DeviceMPS, ops::Vector{Matrix{ComplexF64}}, j::Int)
+    flat = reduce(vcat, [vec(permutedims(o)) for o in ops])
+    out = Vector{ComplexF64}(undef, length(ops))
+    GC.@preserve flat out check(dpsi.ctx, ccall((:tevo_bform_expect_site, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), dpsi.h, j - 1, length(ops), flat, out))
+    return out
+end
+
+"Schmidt values of bond j (between sites j and j+1) in the B form."
+function schmidt_values(dpsi::DeviceMPS, j::Int)
+    buf = Vector{Cdouble}(undef, 65536)
+    nout = Ref{Cint}(0)
+    GC.@preserve buf check(dpsi.ctx, ccall((:tevo_mps_get_lambda, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Cdouble}, Cint, Ref{Cint}), dpsi.h, j, buf, length(buf), nout))   # C: bond left of 0-based site j
+    return buf[1:nout[]]
+end
+
+synchronize(ctx::Ctx) = check(ctx, ccall((:tevo_ctx_synchronize, LIB), Cint, (Ptr{Cvoid},), ctx.h))
+
 # ---- TDVP (src/tdvp.jl:52-88) -------------------------------------------------------------------------
 mutable struct DeviceProjMPO
     ctx::Ctx
@@ -213,7 +296,24 @@ function DeviceProjMPO(H::MPO, dpsi::DeviceMPS)
     end
     e = Ref{Ptr{Cvoid}}(C_NULL)
     check(dpsi.ctx, ccall((:tevo_env_create, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), hm, e))
-    return DeviceProjMPO(dpsi.ctx, hm, e[])
+    PH = DeviceProjMPO(dpsi.ctx, hm, e[])
+    finalizer(PH) do x
+        ccall((:tevo_env_free, LIB), Cint, (Ptr{Cvoid},), x.h)
+        ccall((:tevo_mpo_free, LIB), Cint, (Ptr{Cvoid},), x.hmpo)
+    end
+    return PH
+end
+
+"position!(PH, psi, pos) with PH.nsite = nsite (src/tdvp.jl:53,58-59,79-80); twosite!/onesite! call it themselves."
+position!(PH::DeviceProjMPO, dpsi::DeviceMPS, pos::Int; nsite::Int=2) =
+    check(dpsi.ctx, ccall((:tevo_env_position, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint), PH.h, dpsi.h, pos - 1, nsite))
+
+"inner(psi, H, phi) (test/test_tdvp.jl:29-33) on the device."
+function inner(a::DeviceMPS, PH::DeviceProjMPO, b::DeviceMPS)
+    out = Ref{ComplexF64}(0)
+    check(a.ctx, ccall((:tevo_mps_inner_mpo, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{ComplexF64}),
+                       a.h, PH.hmpo, b.h, out))
+    return out[]
 end
 
 "Forward two-site step of the sweep (src/tdvp.jl:58-64); throws like :63 when exponentiate does not converge."
