@@ -90,3 +90,22 @@ def test_callback_gating_host_logic(tevo):
     assert nb.callback_dt() == 0
     with pytest.raises(ValueError):
         tevo.SpecCallback(0.1, 10, bonds=[0, 9])
+
+
+def test_julia_shim_binds_only_declared_symbols():
+    """Every `ccall((:tevo_..., LIB) ...)` in the (unexecuted) Julia shim names a function that include/tevo.h
+    declares and the built library exports; the reference-facing entry points are all bound."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "timeevomps.jl_b200", "julia", "TevoB200.jl")).read()
+    hdr = open(os.path.join(root, "include", "tevo.h")).read()
+    declared = set(re.findall(r"\b(tevo_[a-z0-9_]+)\s*\(", hdr))
+    bound = set(re.findall(r"\(:(tevo_[a-z0-9_]+),\s*LIB\)", jl))
+    assert bound, "no ccall found"
+    assert bound <= declared, sorted(bound - declared)
+    for must in ("tevo_ctx_create", "tevo_mps_create", "tevo_mps_upload_site", "tevo_mps_download_site",
+                 "tevo_apply_gate", "tevo_apply_layer", "tevo_measure_bond", "tevo_mps_orthogonalize",
+                 "tevo_mps_reorthogonalize", "tevo_mps_inner", "tevo_mps_inner_mpo", "tevo_mpo_create",
+                 "tevo_env_create", "tevo_env_position", "tevo_tdvp_twosite", "tevo_tdvp_onesite",
+                 "tevo_mps_normalize_site", "tevo_mps_free", "tevo_env_free", "tevo_mpo_free", "tevo_ctx_destroy"):
+        assert must in bound, must
