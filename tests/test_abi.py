@@ -109,3 +109,28 @@ def test_julia_shim_binds_only_declared_symbols():
                  "tevo_env_create", "tevo_env_position", "tevo_tdvp_twosite", "tevo_tdvp_onesite",
                  "tevo_mps_normalize_site", "tevo_mps_free", "tevo_env_free", "tevo_mpo_free", "tevo_ctx_destroy"):
         assert must in bound, must
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/tevo.h compiles as C99 and as C++17 (no torch / CUDA types in the signatures), and a C program that
+    references entry points links against the built library (no compute call: there is no GPU here)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "tevo.h"\n'
+                   'int main(void) {\n'
+                   '  tevo_trunc t; tevo_spec s; (void)t; (void)s;\n'
+                   '  /* take addresses so that the linker must resolve the symbols */\n'
+                   '  void* p[] = {(void*)tevo_ctx_create, (void*)tevo_apply_gate, (void*)tevo_apply_layer,\n'
+                   '               (void*)tevo_tdvp_twosite, (void*)tevo_tdvp_onesite, (void*)tevo_mps_upload_site};\n'
+                   '  printf("%d %s\\n", (int)(sizeof(p) / sizeof(p[0])), tevo_version());\n'
+                   '  return 0;\n}\n')
+    inc = os.path.join(root, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)],
+                   check=True)
+    libdir = os.path.join(root, "timeevomps.jl_b200")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=gnu99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-ltevo",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[0] == "6" and "libtevo" in out[1:]
