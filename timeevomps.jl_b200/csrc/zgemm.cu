@@ -11,6 +11,7 @@
 // an m8n8k4 fragment, so no planar repack is required.  A complex MAC is 4 real DMMAs:
 //   Cre += Are*Bre ; Cre += (-Aim)*Bim ; Cim += Are*Bim ; Cim += Aim*Bre .
 // CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -66,7 +67,11 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
   }
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+// CONJA / CONJB: -1 = sign taken from the run-time arguments conjA / conjB (default, the validated path);
+// 0 / 1 = compile-time (EXPERIMENTAL, TEVO_ZGEMM_CTSIGN=1, not yet run on hardware): the signs of the imaginary
+// parts then fold into the operand-negation modifiers of DMMA instead of costing 12 FP64 multiplies/negations per
+// k-slice on the pipe the DMMAs use (SASS: the DADD/FSEL/DMUL of the inner loop disappear).
+template <bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
@@ -135,14 +140,14 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
       for (int i = 0; i < 4; ++i) {
         cplx a = a_s[TA::idx(wm + i * 8 + g, kk + tq)];
         are[i] = a.x;
-        aim[i] = sa * a.y;
+        aim[i] = (CONJA < 0) ? sa * a.y : (CONJA ? -a.y : a.y);
         nai[i] = -aim[i];
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         cplx b = b_s[TB::idx(wn + j * 8 + g, kk + tq)];
         bre[j] = b.x;
-        bim[j] = sb * b.y;
+        bim[j] = (CONJB < 0) ? sb * b.y : (CONJB ? -b.y : b.y);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -184,23 +189,46 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   }
 }
 
-template <bool AK, bool BK_>
-void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
-            long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0,
-            int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0, int lower_only = 0) {
+template <bool AK, bool BK_, int CA, int CB>
+void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
+              long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
+              long bsA, long bsB, long bsC, int lower_only) {
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
   static std::once_flag once;
   std::call_once(once, [&]() {
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_, CA, CB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
-  zgemm_dmma_kernel<AK, BK_><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc,
-                                                          splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC,
-                                                          lower_only);
+  zgemm_dmma_kernel<AK, BK_, CA, CB><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta,
+                                                                  C, ldc, splits > 1 ? Kc : K, part_stride, splits,
+                                                                  bsA, bsB, bsC, lower_only);
   TEVO_LAUNCHED();
+}
+
+template <bool AK, bool BK_>
+void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
+            long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0,
+            int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0, int lower_only = 0) {
+  static const bool ctsign = getenv("TEVO_ZGEMM_CTSIGN") != nullptr;
+#define TEVO_ZG_ARGS st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc, part_stride, batch, bsA, \
+                     bsB, bsC, lower_only
+  if (!ctsign) {
+    launch_c<AK, BK_, -1, -1>(TEVO_ZG_ARGS);
+  } else if (conjA) {
+    if (conjB)
+      launch_c<AK, BK_, 1, 1>(TEVO_ZG_ARGS);
+    else
+      launch_c<AK, BK_, 1, 0>(TEVO_ZG_ARGS);
+  } else {
+    if (conjB)
+      launch_c<AK, BK_, 0, 1>(TEVO_ZG_ARGS);
+    else
+      launch_c<AK, BK_, 0, 0>(TEVO_ZG_ARGS);
+  }
+#undef TEVO_ZG_ARGS
 }
 
 __global__ void zscale_matrix_kernel(int M, int N, cplx beta, cplx* C, long ldc) {

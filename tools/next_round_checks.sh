@@ -21,5 +21,9 @@ TEVO_POTRF_SMEM=1 timeout 60 python tools/dev_hop.py 2>&1 | tail -1
 echo "== back-transformation: pairs of panels (default) vs single panels"
 timeout 60 python tools/dev_heig.py 2048 2>&1 | tail -2
 TEVO_BACK64=1 timeout 60 python tools/dev_heig.py 2048 2>&1 | tail -2
+echo "== ZGEMM with compile-time conjugation signs (experimental) vs default: tests, then timing"
+TEVO_ZGEMM_CTSIGN=1 timeout 120 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "zgemm or split or heig" 2>&1 | tail -3
+timeout 60 python tools/dev_zgemm.py 2>&1 | tail -6
+TEVO_ZGEMM_CTSIGN=1 timeout 60 python tools/dev_zgemm.py 2>&1 | tail -6
 echo "== cluster barrier micro-benchmark"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/cluster_bar_bench proto/cluster_bar_bench.cu && timeout 20 /tmp/cluster_bar_bench
