@@ -23,7 +23,7 @@ timeout 60 python tools/dev_heig.py 2048 2>&1 | tail -2
 TEVO_BACK64=1 timeout 60 python tools/dev_heig.py 2048 2>&1 | tail -2
 echo "== ZGEMM with compile-time conjugation signs (experimental) vs default: tests, then timing"
 TEVO_ZGEMM_CTSIGN=1 timeout 120 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "zgemm or split or heig" 2>&1 | tail -3
-timeout 60 python tools/dev_zgemm.py 2>&1 | tail -6
-TEVO_ZGEMM_CTSIGN=1 timeout 60 python tools/dev_zgemm.py 2>&1 | tail -6
+timeout 120 python tools/dev_time.py 1024 24 2>&1 | tail -1      # per-phase device times of TEBD4 layers at chi=1024
+TEVO_ZGEMM_CTSIGN=1 timeout 120 python tools/dev_time.py 1024 24 2>&1 | tail -1
 echo "== cluster barrier micro-benchmark"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/cluster_bar_bench proto/cluster_bar_bench.cu && timeout 20 /tmp/cluster_bar_bench
