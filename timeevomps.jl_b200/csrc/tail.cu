@@ -125,25 +125,44 @@ __global__ void __launch_bounds__(TNT, 1) tridiag_tail_kernel(TailArgs a) {
     __syncthreads();
     // the reflector goes to column t0+c of A (zeros on and above the diagonal row), spread over the cluster
     for (int i = (int)rank * TNT + tid; i < m; i += C * TNT) a.A[(long)(t0 + c) * a.lda + t0 + i] = vs[i];
-    // ---- (B) fused pass over the own rows
-    for (int s = warp; s < slots; s += TNT / 32) {
-      const int i = s * C + (int)rank;
-      if (i >= m || i <= c) continue;  // warp-uniform
-      cplx* row = Ar + (size_t)s * ldr;
-      const cplx vpi = vp[i], wpi = wp[i];
-      cplx acc = mk(0, 0);
-      for (int j = c + 1 + lane; j < m; j += 32) {
-        cplx aij = row[j];
-        // A(i,j) -= v_p(i) conj(w_p(j)) + w_p(i) conj(v_p(j))
-        const cplx wj = wp[j], vj = vp[j];
-        aij.x -= vpi.x * wj.x + vpi.y * wj.y + wpi.x * vj.x + wpi.y * vj.y;
-        aij.y -= vpi.y * wj.x - vpi.x * wj.y + wpi.y * vj.x - wpi.x * vj.y;
-        row[j] = aij;
-        cfma(acc, aij, vs[j]);
+    // ---- (B) fused pass over the own rows: a warp works on up to four of its rows at a time so that v, v_p, w_p of a
+    // column are read from shared memory once per four matrix elements
+    for (int q0 = 0; warp + (TNT / 32) * q0 < slots; q0 += 4) {
+      cplx* row[4];
+      bool on[4];
+      int ri[4];
+      cplx vpi[4], wpi[4], acc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int s = warp + (TNT / 32) * (q0 + q);
+        const int i = s * C + (int)rank;
+        on[q] = (s < slots) && (i < m) && (i > c);  // warp-uniform
+        ri[q] = i;
+        row[q] = Ar + (size_t)(on[q] ? s : 0) * ldr;
+        vpi[q] = on[q] ? vp[i] : mk(0, 0);
+        wpi[q] = on[q] ? wp[i] : mk(0, 0);
+        acc[q] = mk(0, 0);
       }
-      acc.x = warp_sum(acc.x);
-      acc.y = warp_sum(acc.y);
-      if (lane < C) peer_ptr<C>(ys, lane)[i] = acc;
+      for (int j = c + 1 + lane; j < m; j += 32) {
+        const cplx wj = wp[j], vj = vp[j], vsj = vs[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (!on[q]) continue;
+          cplx aij = row[q][j];
+          // A(i,j) -= v_p(i) conj(w_p(j)) + w_p(i) conj(v_p(j))
+          aij.x -= vpi[q].x * wj.x + vpi[q].y * wj.y + wpi[q].x * vj.x + wpi[q].y * vj.y;
+          aij.y -= vpi[q].y * wj.x - vpi[q].x * wj.y + wpi[q].y * vj.x - wpi[q].x * vj.y;
+          row[q][j] = aij;
+          cfma(acc[q], aij, vsj);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (!on[q]) continue;
+        acc[q].x = warp_sum(acc[q].x);
+        acc[q].y = warp_sum(acc[q].y);
+        if (lane < C) peer_ptr<C>(ys, lane)[ri[q]] = acc[q];
+      }
     }
     cluster_barrier<C>();
     // ---- (C) w and the next column
