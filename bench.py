@@ -20,6 +20,8 @@ import sys
 import threading
 import time
 
+T_PROCESS_START = time.time()
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -32,8 +34,16 @@ UNIT = "steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=2, help="upper bound on the timed steps (see --budget)")
+    ap.add_argument("--warmup", type=int, default=3, help="upper bound on the warm-up steps (see --budget)")
+    ap.add_argument("--budget", type=float, default=float(os.environ.get("TEVO_BENCH_BUDGET_S", "540")),
+                    help="wall-clock budget of the whole run in seconds (env TEVO_BENCH_BUDGET_S).  A TEBD4 step at "
+                         "N=256, chi=1024 takes tens of seconds, so --steps/--warmup are upper bounds: the first "
+                         "warm-up step is timed and the counts are cut so that the run (warm-up, timed steps, one "
+                         "end-to-end step, CPU sample) ends inside the budget.  The JSON line reports the counts "
+                         "actually used (steps, warmup) and the requested ones (steps_requested, warmup_requested)")
+    ap.add_argument("--no-parallel-mode", action="store_true",
+                    help="at 1 GPU: skip the extra `parallel_mode` object (layer-parallel mode on the same chain)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nsites", type=int, default=256)
     ap.add_argument("--chi", type=int, default=1024)
@@ -183,28 +193,130 @@ def workload_string(args):
             % (gates_per_step(args.nsites), args.model, args.nsites, args.chi, args.dt))
 
 
+class Budget:
+    """Wall-clock budget of the whole process (--budget / TEVO_BENCH_BUDGET_S).  --steps / --warmup are upper bounds."""
+
+    def __init__(self, seconds):
+        self.total = float(seconds)
+
+    def elapsed(self):
+        return time.time() - T_PROCESS_START
+
+    def left(self):
+        return self.total - self.elapsed()
+
+    def plan(self, t_step, warm_done, warm_req, steps_req, reserve):
+        """How many more warm-up steps and how many timed steps fit: at least one timed step; three warm-up steps in
+        total (the timing rule) before a second timed step is added; never more than requested."""
+        avail = self.left() - reserve
+        n = max(int(avail // max(t_step, 1e-9)), 1)            # steps that still fit
+        warm_more = max(0, min(warm_req - warm_done, max(min(3 - warm_done, n - 1), n - steps_req)))
+        timed = max(1, min(steps_req, n - warm_more))
+        return warm_more, timed
+
+
+def debug_counters(ctx):
+    import ctypes as C
+    from timeevomps_jl_b200._lib import load as _load
+    out = (C.c_double * 16)()
+    _load().tevo_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    _load().tevo_debug_counters(ctx.h, out, 16)
+    return list(out)
+
+
+def read_peaks():
+    peaks, fp64 = {}, {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    try:
+        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    return hbm, src, float(fp64.get("zgemm_tflops_sustained", 36.8))
+
+
+def panel_roofline(prof, c0, c1, hbm_peak, peak_src, label="tridiag_panel_kernel"):
+    """Roofline object of the dominant kernel.  Numerator = the library's own count of the algorithmic bytes of the
+    tridiagonalisation panels it launched inside the timed region (one read of the trailing matrix per column:
+    sum over launches of pw x (n - p0)^2 x 16 B, tevo_debug_counters[13]); denominator = the CUDA-event time of those
+    launches (in-library per-phase events on the library stream)."""
+    if "tridiag_panel" not in prof:
+        return None
+    tk = prof["tridiag_panel"]
+    bytes_alg = c1[13] - c0[13]
+    nfact = int(c1[12] - c0[12])
+    nlaunch = int(c1[14] - c0[14])
+    ach = bytes_alg / (tk["ms"] * 1e-3) / 1e9
+    traffic, tsrc = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_panel_traffic.json")))
+        traffic, tsrc = tj["dram_bytes_per_launch"], tj.get("source")
+    except Exception:
+        pass
+    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+            "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_alg / max(nlaunch, 1), "launches": nlaunch,
+            "factorisations": nfact, "avg_launch_ms": tk["ms"] / max(tk["count"], 1),
+            "share_of_step": tk["ms"] / total_prof,
+            "limiter": "latency, not bandwidth: every column of the Householder tridiagonalisation is a chain of two "
+                       "grid-wide barriers and dependent L2 round trips; the trailing matrix stays L2-resident inside a "
+                       "launch, so DRAM sees it about once per 64 columns (traffic) while the matrix-vector products "
+                       "read it once per column (algorithmic bytes).  The HBM roof is the contract's denominator; the "
+                       "kernel cannot reach it by construction of the one-stage algorithm"}
+
+
+def emit(line):
+    sys.stdout.write(json.dumps(line) + "\n")
+    sys.stdout.flush()
+
+
 def run_reference(args):
+    """Reference arm: the CPU restatement of the reference path (oracle/) on all host BLAS threads.  One "step" of this
+    arm = REF_UPDATES interior two-site updates at the benchmark's chi (a bounded sample of the 1275 updates of one
+    TEBD4 step), extrapolated by the update count; --steps/--warmup are cut to the wall-clock budget."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    REF_UPDATES = 2
+    budget = Budget(min(args.budget, 300.0))
     arm = CpuArm(args)
-    vals = []
-    cb = None
-    for _ in range(args.warmup + args.steps):
-        cb = arm.sample(1)
+    first = arm.sample(REF_UPDATES)
+    t_step = REF_UPDATES / (first["value"] * gates_per_step(args.nsites))
+    warm_more, timed = budget.plan(t_step, 1, max(args.warmup, 1), args.steps, reserve=5.0)
+    for _ in range(warm_more):
+        arm.sample(REF_UPDATES)
+    vals, cb = [], first
+    for _ in range(timed):
+        cb = arm.sample(REF_UPDATES)
         vals.append(cb["value"])
-    timed = vals[args.warmup:] or vals[-1:]
-    v = float(1.0 / np.mean([1.0 / x for x in timed]))
+    v = float(1.0 / np.mean([1.0 / x for x in vals]))
     cb["value"] = v
     cb["sample"] = "each step = " + cb["sample"]
-    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    cb["per_step_values"] = [float(x) for x in vals]
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": timed, "warmup": 1 + warm_more,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_string(args), "mode": "sequential (reference-faithful centre moves)",
                        "parallelism": "host CPU, all BLAS threads"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def pinned_copy(torch, arrays):
+    out = []
+    for a in arrays:
+        buf = torch.empty(max(a.size, 1) * 2, dtype=torch.float64, pin_memory=True)
+        v = buf.numpy()[:a.size * 2].view(np.complex128).reshape(a.shape, order="F")
+        v[...] = a
+        out.append(v)
+    return out
 
 
 def run_sharded(args):
@@ -216,6 +328,7 @@ def run_sharded(args):
     import tevo_b200 as t
     from timeevomps_jl_b200 import replicas
     from timeevomps_jl_b200.sharded import DeviceSegment, ShardedTEBD, segment_bounds
+    budget = Budget(args.budget)
     rank, world, local = replicas.world()
     torch.cuda.set_device(local)
     dist = None
@@ -225,10 +338,8 @@ def run_sharded(args):
     ctx = t.default_ctx()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     N, chi = args.nsites, args.chi
-    glob = t.MPS.random(N, chi, seed=0).to_bform()      # same state on every rank; each keeps its segment
     lo, hi = segment_bounds(N, world, rank)
-    seg = DeviceSegment(glob, lo, hi, ghost=(rank < world - 1))
-    del glob
+    seg = DeviceSegment.random(N, chi, lo, hi, ghost=(rank < world - 1), seed=0)
     sh = ShardedTEBD(seg, N, dist, rank, world, device="cuda")
     Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
     kw = dict(maxdim=chi, mindim=chi)
@@ -244,7 +355,20 @@ def run_sharded(args):
 
     for U in Ustart:
         sh.apply_layer(U, **kw)
-    for _ in range(args.warmup):
+    barrier()
+    t0 = time.perf_counter()
+    step()
+    barrier()
+    t_step = replicas.max_over_ranks(time.perf_counter() - t0, dist, device="cuda")
+    elapsed = replicas.max_over_ranks(budget.elapsed(), dist, device="cuda")
+    budget.total -= max(0.0, elapsed - budget.elapsed())       # all ranks plan with the slowest rank's clock
+    reserve = 15.0 + (0.0 if args.no_e2e else 1.3 * t_step + 10.0)
+    warm_more, timed = budget.plan(t_step, 1, max(args.warmup, 1), args.steps, reserve)
+    if dist is not None:      # identical counts on every rank
+        tt = torch.tensor([warm_more, timed], dtype=torch.int64, device="cuda")
+        dist.broadcast(tt, 0)
+        warm_more, timed = int(tt[0].item()), int(tt[1].item())
+    for _ in range(warm_more):
         step()
     barrier()
     sampler = ClockSampler(local)
@@ -252,105 +376,92 @@ def run_sharded(args):
         sampler.start()
     t.profile_enable(True)
     t.profile_read(reset=True)
+    c0 = debug_counters(ctx)
     n0 = ctx.launch_count()
     b0 = sh.bytes_sent
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(timed):
         step()
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
+    # the boundary exchange runs on torch's stream, ordered with the library stream by events, so the device time of
+    # the region is the larger of the event span on the library stream and the synchronised wall clock of the slowest rank
     ms = max(e0.elapsed_time(e1), 0.0)
     ms = replicas.max_over_ranks(ms, dist, device="cuda")
     launches = ctx.launch_count() - n0
     prof = t.profile_read(reset=True)
     t.profile_enable(False)
+    c1 = debug_counters(ctx)
     clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms / args.steps
+    ms_per_step = ms / timed
     value = 1e3 / ms_per_step
-    # end to end: segment uploaded from pinned host memory, one step, segment downloaded - every step
+    bytes_per_step = int((sh.bytes_sent - b0) / max(timed, 1))
+    # end to end: segment uploaded from pinned host memory, one step, segment downloaded
     e2e = None
     if not args.no_e2e:
         import ctypes as C
         from timeevomps_jl_b200._lib import load as _load, check as _check
         nl = seg.nloc + (1 if rank < world - 1 else 0)
-        host = [seg.psi.site(i) for i in range(nl)]
+        pinned = pinned_copy(torch, [seg.psi.site(i) for i in range(nl)])
         lams = [seg.psi.schmidt_values(i) for i in range(nl + 1)]
-        pinned = []
-        for a in host:
-            buf = torch.empty(a.size * 2, dtype=torch.float64, pin_memory=True)
-            v = buf.numpy().view(np.complex128).reshape(a.shape, order="F")
-            v[...] = a
-            pinned.append(v)
         nbytes = sum(a.nbytes for a in pinned) + sum(l.nbytes for l in lams)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            for i, a in enumerate(pinned):
-                seg.psi.set_site(i, a)
-            for i, l in enumerate(lams):
-                _check(_load().tevo_mps_set_lambda(seg.psi.h, i, len(l), l.ctypes.data_as(C.POINTER(C.c_double))), ctx.h)
-            _check(_load().tevo_mps_mark_bform(seg.psi.h, 1), ctx.h)
-            step()
-            for i in range(nl):
-                out = seg.psi.site(i)
-                if out.shape == pinned[i].shape:
-                    pinned[i][...] = out
-            lams = [seg.psi.schmidt_values(i) for i in range(nl + 1)]
+        for i, a in enumerate(pinned):
+            seg.psi.set_site(i, a)
+        for i, l in enumerate(lams):
+            _check(_load().tevo_mps_set_lambda(seg.psi.h, i, len(l), l.ctypes.data_as(C.POINTER(C.c_double))), ctx.h)
+        _check(_load().tevo_mps_mark_bform(seg.psi.h, 1), ctx.h)
+        step()
+        for i in range(nl):
+            out = seg.psi.site(i)
+            if out.shape == pinned[i].shape:
+                pinned[i][...] = out
+        lams = [seg.psi.schmidt_values(i) for i in range(nl + 1)]
         barrier()
         dt_e2e = replicas.max_over_ranks(time.perf_counter() - t0, dist, device="cuda")
-        e2e = {"value": args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": int(nbytes)}
+        e2e = {"value": 1.0 / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(nbytes), "steps": 1}
     if rank != 0:
         return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
-    roofline = None
-    if "tridiag_panel" in prof:
-        d = 2
-        dims = [min(d ** min(j, N - j, 40), chi) for j in range(N + 1)]
-        sizes = [d * dims[g.b + 2] for U in Us for g in U if lo <= g.b < hi]    # rho = theta^+ theta is n x n
-        bytes_alg = sum(16.0 * s ** 3 / 3.0 for s in sizes) * args.steps
-        tk = prof["tridiag_panel"]
-        ach = bytes_alg / (tk["ms"] * 1e-3) / 1e9
-        roofline = {"kernel": "tridiag_panel_kernel (rank 0)", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "launches": tk["count"],
-                    "avg_launch_ms": tk["ms"] / tk["count"], "share_of_step": tk["ms"] / total_prof}
+    hbm_peak, peak_src, zpeak = read_peaks()
+    roofline = panel_roofline(prof, c0, c1, hbm_peak, peak_src, "tridiag_panel_kernel (rank 0)")
+    flops_step = algorithmic_flops_per_gate(chi) * gates_per_step(N)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": timed, "warmup": 1 + warm_more,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic",
         "config": {"workload": workload_string(args),
                    "mode": "layer-parallel (Hastings B-form) TEBD: NOT the sequential reference algorithm; equal to it "
-                           "without truncation, O(discarded weight) apart with it",
+                           "without truncation, O(discarded weight) apart with it.  The 1-GPU line reports this mode "
+                           "as `parallel_mode` beside the sequential `value`: scaling efficiency is value(N) / "
+                           "(N x parallel_mode.value)",
                    "parallelism": ("1 GPU" if world == 1 else
                                    "chain split into %d contiguous segments, one per GPU; boundary tensor + Schmidt "
                                    "values exchanged per cut bond and layer by NCCL send/recv" % world),
                    "l2_policy": "inputs larger than L2 (segment of an 8 GiB MPS streamed per step)"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "boundary_bytes_sent_per_step_rank0": int((sh.bytes_sent - b0) / max(args.steps, 1)),
-        "wall_ms_per_step": wall * 1e3 / args.steps,
+        "fp64_tensor": {"algorithmic_tflops": flops_step / (ms_per_step * 1e-3) / 1e12, "peak_tflops": zpeak * world,
+                        "frac": flops_step / (ms_per_step * 1e-3) / 1e12 / (zpeak * world)},
+        "boundary_bytes_sent_per_step_rank0": bytes_per_step,
+        "wall_ms_per_step": wall * 1e3 / timed,
         "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "budget_s": args.budget, "wall_s": round(budget.elapsed(), 1),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_tdvp(args):
     """Secondary workload: one two-site TDVP step (right + left sweep, src/tdvp.jl:54-95) of the XXZ chain at the
     BASELINE config-4 shape (default N=64 via --nsites, chi=1024, krylovdim=30, exp_tol=1e-12); one independent
     h value per GPU (replicas).  Reported as an extra JSON line for profiles/, not the headline metric."""
-    import ctypes as C
     import torch
     import tevo_b200 as t
     from timeevomps_jl_b200 import replicas
-    from timeevomps_jl_b200._lib import load as _load
     rank, world, local = replicas.world()
     torch.cuda.set_device(local)
     if world > 1:
@@ -370,9 +481,7 @@ def run_tdvp(args):
     ctx.synchronize()
     if dist is not None:
         dist.barrier()
-    out0 = (C.c_double * 12)()
-    _load().tevo_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-    _load().tevo_debug_counters(ctx.h, out0, 12)
+    c0 = debug_counters(ctx)
     t.profile_enable(True)
     t.profile_read(reset=True)
     st = {}
@@ -388,17 +497,11 @@ def run_tdvp(args):
         dist.barrier()
     ms = replicas.max_over_ranks(e0.elapsed_time(e1), dist, device="cuda")
     prof = t.profile_read(reset=True)
-    out1 = (C.c_double * 12)()
-    _load().tevo_debug_counters(ctx.h, out1, 12)
+    c1 = debug_counters(ctx)
     if rank != 0:
         return
-    fp64 = {}
-    try:
-        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
-    except Exception:
-        pass
-    zpeak = float(fp64.get("zgemm_tflops_sustained", 36.8))
-    heff_flops = out1[11] - out0[11]
+    _, _, zpeak = read_peaks()
+    heff_flops = c1[11] - c0[11]
     hk = prof.get("heff_apply", {"ms": 0.0, "count": 0})
     ach = heff_flops / (hk["ms"] * 1e-3) / 1e12 if hk["ms"] else None
     line = {"metric": "tdvp_time_steps_per_sec", "value": world * args.steps * 1e3 / ms, "unit": UNIT, "n_gpus": world,
@@ -413,7 +516,184 @@ def run_tdvp(args):
                          "traffic": None, "peak_source": "measured cuBLAS ZGEMM 4096^3 (profiles/r01_fp64_peaks.json)",
                          "share_of_step": hk["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0)},
             "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def run_sequential(args):
+    """The headline: the reference's own algorithm (gates of a layer applied sequentially, centre moved between gates)
+    on one GPU; with torchrun and --mode sequential, one independent trajectory per GPU (replicas, no collective)."""
+    import torch
+    import tevo_b200 as t
+    from timeevomps_jl_b200 import replicas
+    budget = Budget(args.budget)
+    rank, world, local = replicas.world()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = t.default_ctx()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
+    N, chi = args.nsites, args.chi
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    psi = t.MPS.random(N, chi, seed=replicas.trajectory_seed(rank))
+    ctx.synchronize()
+    Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
+    kw = dict(maxdim=chi, mindim=chi)
+    state = {"rev": False, "psi": psi}
+
+    def layer(U):
+        t.apply_gates(state["psi"], U, reversed=state["rev"], **kw)
+        state["rev"] = not state["rev"]
+
+    def step():
+        for U in Us:
+            layer(U)
+
+    for U in Ustart:
+        layer(U)
+    barrier()
+    t0 = time.perf_counter()
+    step()                                     # warm-up step 1, wall-timed: sizes the rest of the run
+    barrier()
+    t_step = replicas.max_over_ranks(time.perf_counter() - t0, dist, device="cuda")
+    want_par = (world == 1) and not args.no_parallel_mode
+    reserve = 20.0
+    if not args.no_e2e:
+        reserve += 1.2 * t_step + 15.0         # one step + 2 x 8 GiB over PCIe
+    if not args.no_cpu:
+        reserve += 15.0
+    if want_par:
+        reserve += 2 * 0.75 * t_step + 15.0    # one warm-up + one timed layer-parallel step + the B-form conversion
+    warm_more, timed = budget.plan(t_step, 1, max(args.warmup, 1), args.steps, reserve)
+    if dist is not None:
+        tt = torch.tensor([warm_more, timed], dtype=torch.int64, device="cuda")
+        dist.broadcast(tt, 0)
+        warm_more, timed = int(tt[0].item()), int(tt[1].item())
+    for _ in range(warm_more):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t.profile_enable(True)
+    t.profile_read(reset=True)
+    c0 = debug_counters(ctx)
+    n0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(timed):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    prof = t.profile_read(reset=True)
+    t.profile_enable(False)
+    c1 = debug_counters(ctx)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = replicas.max_over_ranks(ms, dist, device="cuda")
+    ms_per_step = ms / timed
+    value = world * 1e3 / ms_per_step
+
+    # ---- end-to-end through the public API with host buffers: upload, one step, download ----
+    e2e = None
+    if not args.no_e2e:
+        psi = state["psi"]
+        pinned = pinned_copy(torch, psi.tensors())
+        nbytes = sum(a.nbytes for a in pinned)
+        llim, rlim = psi.limits()
+        state["psi"] = None
+        del psi
+        barrier()
+        t0 = time.perf_counter()
+        state["psi"] = t.MPS.from_tensors(pinned, llim=llim, rlim=rlim)
+        step()
+        out = state["psi"].tensors()
+        for dst, src in zip(pinned, out):
+            if dst.shape == src.shape:
+                dst[...] = src
+        del out
+        barrier()
+        dt_e2e = replicas.max_over_ranks(time.perf_counter() - t0, dist, device="cuda")
+        e2e = {"value": world / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
+               "d2h_bytes_per_step": int(nbytes), "steps": 1}
+        del pinned
+
+    # ---- the same chain in the layer-parallel mode (what the >1-GPU runs shard): reference point for scaling ----
+    parallel_mode = None
+    if want_par and budget.left() > 2 * 0.75 * t_step + 30.0:
+        from timeevomps_jl_b200.tebd import apply_gates_parallel
+        psi = state["psi"]
+        psi.to_bform()
+
+        def pstep():
+            for U in Us:
+                apply_gates_parallel(psi, U, **kw)
+
+        barrier()
+        t0 = time.perf_counter()
+        pstep()
+        barrier()
+        tp1 = time.perf_counter() - t0
+        npar = 1 if budget.left() < 2.2 * tp1 + 30.0 else 2
+        nl0 = ctx.launch_count()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(npar):
+            pstep()
+        p1.record(stream)
+        barrier()
+        pms = p0.elapsed_time(p1) / npar
+        parallel_mode = {"value": 1e3 / pms, "unit": UNIT, "ms_per_step": pms, "steps": npar, "warmup": 1,
+                         "gpu_launches": int(ctx.launch_count() - nl0),
+                         "mode": "layer-parallel (Hastings B-form), the mode `bench.py --gpus N>1` shards; divide "
+                                 "value(N) by N x this value for the scaling efficiency in the same mode"}
+    if rank != 0:
+        return
+    hbm_peak, peak_src, zgemm_peak = read_peaks()
+    roofline = panel_roofline(prof, c0, c1, hbm_peak, peak_src)
+    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
+    flops_step = algorithmic_flops_per_gate(chi) * gates_per_step(N)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": timed, "warmup": 1 + warm_more,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic",
+        "config": {"workload": workload_string(args),
+                   "mode": "sequential (reference-faithful centre moves)",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent trajectories (replicas), no collective" % world,
+                   "l2_policy": "inputs larger than L2 (8 GiB of MPS streamed per step)"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+        "fp64_tensor": {"algorithmic_tflops": flops_step / (ms_per_step * 1e-3) / 1e12, "peak_tflops": zgemm_peak,
+                        "frac": flops_step / (ms_per_step * 1e-3) / 1e12 / zgemm_peak,
+                        "note": "SURVEY 8(d) conservative numerator (theta + gate + factor GEMMs) over measured cuBLAS "
+                                "ZGEMM peak"},
+        "parallel_mode": parallel_mode,
+        "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}, "dominant_phase": dom,
+        "phase_share": {k: round(v["ms"] / total_prof, 4) for k, v in prof.items()},
+        "centre_moves": {"cholqr_single_pass": int(c1[0] - c0[0]), "cholqr_two_pass": int(c1[1] - c0[1]),
+                         "eigen_fallback": int(c1[2] - c0[2]), "note": "inside the timed region"},
+        "budget_s": args.budget,
+    }
+    if not args.no_cpu:
+        arm = CpuArm(args)
+        one = arm.sample(1)
+        per_gate = 1.0 / (one["value"] * gates_per_step(N))
+        more = int(max(0, min(args.cpu_sample_gates - 1, (min(budget.left(), 40.0) - 5.0) // max(per_gate, 1e-3))))
+        line["cpu_baseline"] = arm.sample(more) if more > 0 else one
+        if args.cpu_1thread:
+            # SURVEY 8(d): the baseline is stated for all BLAS threads (value, cores) and for one thread
+            line["cpu_baseline"].update(arm.sample_one_thread())
+    line["wall_s"] = round(budget.elapsed(), 1)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -429,176 +709,7 @@ def main():
     if args.mode == "parallel" or (args.mode == "auto" and world_env > 1):
         run_sharded(args)
         return
-    import torch
-    import tevo_b200 as t
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = t.default_ctx()
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    N, chi = args.nsites, args.chi
-
-    def barrier():
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    from timeevomps_jl_b200 import replicas
-    psi = t.MPS.random(N, chi, seed=replicas.trajectory_seed(rank))
-    ctx.synchronize()
-    Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
-    kw = dict(maxdim=chi, mindim=chi)
-    state = {"rev": False}
-
-    def layer(U):
-        t.apply_gates(psi, U, reversed=state["rev"], **kw)
-        state["rev"] = not state["rev"]
-
-    def step():
-        for U in Us:
-            layer(U)
-
-    for U in Ustart:
-        layer(U)
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t.profile_enable(True)
-    t.profile_read(reset=True)
-    n0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    launches = ctx.launch_count() - n0
-    ms = e0.elapsed_time(e1)
-    prof = t.profile_read(reset=True)
-    t.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = replicas.max_over_ranks(ms, dist if world > 1 else None, device="cuda")
-    ms_per_step = ms / args.steps
-    value = world * 1e3 / ms_per_step
-
-    # ---- end-to-end through the public API with host buffers (upload + step + download every step) ----
-    e2e = None
-    if not args.no_e2e:
-        host = psi.tensors()
-        pinned = []
-        for a in host:
-            buf = torch.empty(a.size * 2, dtype=torch.float64, pin_memory=True)
-            v = buf.numpy().view(np.complex128).reshape(a.shape, order="F")
-            v[...] = a
-            pinned.append(v)
-        nbytes = sum(a.nbytes for a in pinned)
-        llim, rlim = psi.limits()
-        del psi
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            psi = t.MPS.from_tensors(pinned, llim=llim, rlim=rlim)
-            step()
-            out = psi.tensors()
-            llim, rlim = psi.limits()
-            for dst, src in zip(pinned, out):
-                if dst.shape == src.shape:
-                    dst[...] = src
-            del out
-        barrier()
-        dt_e2e = time.perf_counter() - t0
-        dt_e2e = replicas.max_over_ranks(dt_e2e, dist if world > 1 else None, device="cuda")
-        e2e = {"value": world * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(nbytes),
-               "d2h_bytes_per_step": int(nbytes)}
-
-    if rank != 0:
-        return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    fp64 = {}
-    try:
-        fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")))
-    except Exception:
-        pass
-    zgemm_peak = float(fp64.get("zgemm_tflops_sustained", 36.8))
-    total_prof = sum(v["ms"] for v in prof.values()) or 1.0
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0] if prof else None
-    roofline = None
-    if "tridiag_panel" in prof:
-        # dominant kernel: Householder tridiagonalisation panel (HEMV-bound).  Algorithmic bytes of one launch =
-        # one read of the trailing matrix per column = 64 columns x (n - p0)^2 x 16 B; summed over the launches of
-        # the timed region analytically: every factorisation of size n reads 16 n^3 / 3 bytes.
-        d = 2
-        sizes = []
-        dims = [min(d ** min(j, N - j, 40), chi) for j in range(N + 1)]
-        for U in Us:
-            for g in U:
-                b = g.b
-                m, n = dims[b] * d, d * dims[b + 2]
-                sizes.append(m)                                  # split: rho is m x m (left) / n x n (right)
-                sizes.append(min(dims[b + 1] * d, dims[b + 2]))  # centre move: Gram matrix of the small side
-        bytes_alg = sum(16.0 * s ** 3 / 3.0 for s in sizes) * args.steps
-        tk = prof["tridiag_panel"]
-        ach = bytes_alg / (tk["ms"] * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_panel_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        roofline = {"kernel": "tridiag_panel_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bytes_alg / max(tk["count"], 1),
-                    "note": "latency-bound panel kernel: the trailing matrix is L2-resident within a launch, so DRAM "
-                            "traffic (ncu, profiles/r01_panel_traffic.json) is ~1 matrix per launch although 64 "
-                            "matrix-vector products read it algorithmically",
-                    "launches": tk["count"], "avg_launch_ms": tk["ms"] / tk["count"],
-                    "share_of_step": tk["ms"] / total_prof}
-    flops_step = algorithmic_flops_per_gate(chi) * gates_per_step(N)
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
-        "data": "synthetic",
-        "config": {"workload": workload_string(args),
-                   "mode": "sequential (reference-faithful centre moves)",
-                   "parallelism": "1 GPU" if world == 1 else "%d independent trajectories (replicas), no collective" % world,
-                   "l2_policy": "inputs larger than L2 (8 GiB of MPS streamed per step)"},
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "fp64_tensor": {"algorithmic_tflops": flops_step / (ms_per_step * 1e-3) / 1e12, "peak_tflops": zgemm_peak,
-                        "frac": flops_step / (ms_per_step * 1e-3) / 1e12 / zgemm_peak,
-                        "note": "SURVEY 8(d) conservative numerator (theta + gate + factor GEMMs) over measured cuBLAS "
-                                "ZGEMM peak"},
-        "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}, "dominant_phase": dom,
-    }
-    try:
-        import ctypes as C
-        from timeevomps_jl_b200._lib import load as _load
-        out = (C.c_double * 11)()
-        _load().tevo_debug_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-        _load().tevo_debug_counters(ctx.h, out, 11)
-        line["centre_moves"] = {"cholqr_single_pass": int(out[0]), "cholqr_two_pass": int(out[1]),
-                                "eigen_fallback": int(out[2]), "note": "cumulative since context creation"}
-    except Exception:
-        pass
-    if not args.no_cpu:
-        arm = CpuArm(args)
-        line["cpu_baseline"] = arm.sample(args.cpu_sample_gates)
-        if args.cpu_1thread:
-            # the baseline is stated for all BLAS threads (value, cores) and for one thread
-            line["cpu_baseline"].update(arm.sample_one_thread())
-    print(json.dumps(line))
+    run_sequential(args)
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <atomic>
+#include <mutex>
 #include <string>
 
 namespace tevo {
@@ -55,6 +56,32 @@ struct TevoError {
   int code;
   std::string msg;
   TevoError(int c, std::string m) : code(c), msg(std::move(m)) {}
+};
+
+// cudaFuncSetAttribute and friends are per DEVICE: run a set-up lambda once for every device a launch path is used
+// on (a process may hold contexts on several GPUs through tevo_ctx_create(device)).
+struct PerDeviceOnce {
+  static constexpr int MAXDEV = 64;
+  std::mutex mu;
+  std::atomic<bool> done[MAXDEV];
+  PerDeviceOnce() {
+    for (auto& d : done) d.store(false);
+  }
+  template <class F>
+  void operator()(F&& f) {
+    int dev = 0;
+    TEVO_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAXDEV) {
+      f();
+      return;
+    }
+    if (done[dev].load(std::memory_order_acquire)) return;
+    std::lock_guard<std::mutex> g(mu);
+    if (!done[dev].load(std::memory_order_relaxed)) {
+      f();
+      done[dev].store(true, std::memory_order_release);
+    }
+  }
 };
 
 // warp / block reductions (double)

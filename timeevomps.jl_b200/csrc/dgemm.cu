@@ -118,8 +118,8 @@ void dgemm_merge(cudaStream_t st, const MergeDesc* descs_dev, const int* K_dev, 
                  const double* B, double* C, long ld) {
   if (nmerge <= 0) return;
   const size_t smem = (size_t)STAGES * (BK * (BM + APAD) + BN * (BK + BPAD)) * sizeof(double);
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(dgemm_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
   dim3 grid((maxN + BM - 1) / BM, (maxN + BN - 1) / BN, nmerge);

@@ -6,6 +6,7 @@
 #include "heig.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "prof.h"
@@ -646,6 +647,16 @@ extern "C" int tevo_debug_panel_cycles(unsigned long long* out, int reset) {
 }
 #endif
 
+// algorithmic work of the tridiagonalisation panels launched so far (bench.py's roofline numerator): factorisations,
+// bytes of the matrix-vector products (one read of the trailing matrix per column) and panel launches
+std::atomic<long long> g_heig_calls{0}, g_panel_launches{0};
+std::atomic<double> g_panel_alg_bytes{0.0};
+void heig_counters(double* calls, double* bytes, double* launches) {
+  *calls = (double)g_heig_calls.load();
+  *bytes = g_panel_alg_bytes.load();
+  *launches = (double)g_panel_launches.load();
+}
+
 void Heig::init() {
   int dev = 0;
   TEVO_CUDA_CHECK(cudaGetDevice(&dev));
@@ -700,13 +711,14 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   n_ = n;
   A_ = A;
   lda_ = lda;
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(tridiag_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PANEL_SMEM));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(wy_T_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(2 * sizeof(cplx) * TRB * TRB)));
   });
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
+  g_heig_calls.fetch_add(1, std::memory_order_relaxed);
   double* zero_from = acc_;  // the barrier counter and the replicated accumulators are cleared before every panel
   const size_t zero_bytes = sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
@@ -770,6 +782,12 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
       ProfScope ps(st, P_TRI_PANEL);
       TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)tridiag_panel_kernel, dim3(grid), dim3(NT), args, smem, st));
       TEVO_LAUNCHED();
+      g_panel_launches.fetch_add(1, std::memory_order_relaxed);
+      double by = 0.0;
+      for (int i = 0; i < pw; ++i) by += 16.0 * (double)(n - p0 - i - 1) * (double)(n - p0 - i - 1);
+      double cur = g_panel_alg_bytes.load(std::memory_order_relaxed);
+      while (!g_panel_alg_bytes.compare_exchange_weak(cur, cur + by, std::memory_order_relaxed)) {
+      }
     }
     const int q0 = p0 + pw;
     // trailing rank-2k update  A22 -= V W^H + W V^H = [V|W] [W|V]^H

@@ -9,6 +9,9 @@ namespace tevo {
 int tridiag_tail_max_m(int cluster);
 void tridiag_tail(cudaStream_t st, int cluster, int n, int t0, cplx* A, long lda, double* d, double* e, cplx* taus);
 
+// cumulative counters of the tridiagonalisation panels (process-wide): see heig.cu
+void heig_counters(double* calls, double* bytes, double* launches);
+
 class Heig {
  public:
   void init();

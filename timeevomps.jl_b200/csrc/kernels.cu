@@ -406,8 +406,8 @@ void refine_truncate(cudaStream_t st, const double* lam2, int k1, int nfull, con
   while (npow2 < k1) npow2 <<= 1;
   if (npow2 > 8192) throw TevoError(1, "refine_truncate: more than 8192 singular values not supported");
   size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(refine_truncate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
   });
   int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;
@@ -441,8 +441,8 @@ void sort_truncate(cudaStream_t st, const double* lam, int nc, int nfull, const 
   while (npow2 < nc) npow2 <<= 1;
   if (npow2 > 8192) throw TevoError(1, "sort_truncate: more than 8192 singular values not supported");
   size_t smem = (size_t)npow2 * (sizeof(double) + sizeof(int));
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(sort_truncate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
   });
   int threads = npow2 < 1024 ? (npow2 < 32 ? 32 : npow2) : 1024;

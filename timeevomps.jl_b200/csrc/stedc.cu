@@ -536,8 +536,8 @@ void Stedc::run(cudaStream_t st, int n, const double* d, const double* e, double
   ensure(n);
   Plan& plan = plan_for(n);
   const long ld = n;
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(merge_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(zhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

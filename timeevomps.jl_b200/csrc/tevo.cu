@@ -31,6 +31,22 @@ struct tevo_ctx {
   DevBuf ws[8];
   unsigned char* d_small = nullptr;  // staging for gates / operators / offsets (device)
   size_t small_cap = 0;
+  unsigned char* d_heff = nullptr;  // H_eff operator block (P x Q complex + Q offsets), sized to need (make_heff)
+  size_t heff_cap = 0;
+  void* heff_block(size_t bytes) {
+    if (heff_cap < bytes) {
+      if (d_heff) {
+        TEVO_CUDA_CHECK(cudaStreamSynchronize(stream));
+        TEVO_CUDA_CHECK(cudaFree(d_heff));
+      }
+      d_heff = nullptr;
+      heff_cap = 0;
+      const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+      TEVO_CUDA_CHECK(cudaMalloc(&d_heff, want));
+      heff_cap = want;
+    }
+    return d_heff;
+  }
   double* d_scal = nullptr;  // device scalars
   double* h_scal = nullptr;  // pinned mirror
   static constexpr int NSCAL = 1024;
@@ -133,7 +149,8 @@ static thread_local std::string g_static_err;
 
 #define TEVO_TRY(ctxptr) \
   tevo_ctx* _ctx = (ctxptr); \
-  try {
+  try { \
+    if (_ctx) TEVO_CUDA_CHECK(cudaSetDevice(_ctx->device)); /* a process may hold contexts on several GPUs */
 #define TEVO_CATCH                                                                                       \
   }                                                                                                      \
   catch (const tevo::CudaError& e) {                                                                     \
@@ -356,6 +373,7 @@ extern "C" int tevo_ctx_destroy(tevo_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->ones.p) cudaFree(ctx->ones.p);
   if (ctx->d_small) cudaFree(ctx->d_small);
+  if (ctx->d_heff) cudaFree(ctx->d_heff);
   if (ctx->d_scal) cudaFree(ctx->d_scal);
   if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
   ctx->split.destroy();
@@ -964,7 +982,7 @@ struct Heff {
   }
 };
 
-static Heff make_heff(tevo_env* e, tevo_mps* psi, int pos, int nsite, cplx* dev_block /* persistent small buffer */) {
+static Heff make_heff(tevo_env* e, tevo_mps* psi, int pos, int nsite) {
   tevo_ctx* c = e->ctx;
   const tevo_mpo* H = e->H;
   const int d = H->d;
@@ -1018,9 +1036,11 @@ static Heff make_heff(tevo_env* e, tevo_mps* psi, int pos, int nsite, cplx* dev_
       }
     h.n = (long)h.cl * d * h.cr;
   }
-  // persistent (per call) device copy: carve from dev_block
+  // device copy in the context's dedicated block, sized from P and Q (wl*wr*d^4 complex for nsite = 2: beyond 64 KB
+  // already for d = 2 with w >= 16), so that no other staging use of small() can alias or overrun it
   size_t mb = M.size() * sizeof(cplx);
   size_t mba = (mb + 63) & ~(size_t)63;
+  cplx* dev_block = (cplx*)c->heff_block(mba + oq.size() * sizeof(long));
   upload_small(c, dev_block, M.data(), mb);
   upload_small(c, (unsigned char*)dev_block + mba, oq.data(), oq.size() * sizeof(long));
   h.dM = dev_block;
@@ -1034,8 +1054,7 @@ extern "C" int tevo_env_apply_host(tevo_env* env, tevo_mps* psi, int pos, int ns
   require(env && psi && v && out, "tevo_env_apply_host: null argument");
   tevo_ctx* c = env->ctx;
   env_position(env, psi, pos, nsite);
-  cplx* blk = (cplx*)c->small(1 << 16);
-  Heff h = make_heff(env, psi, pos, nsite, blk);
+  Heff h = make_heff(env, psi, pos, nsite);
   cplx* dv = c->get_ws(WS_W, (size_t)2 * h.n);
   TEVO_CUDA_CHECK(cudaMemcpyAsync(dv, v, h.n * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
   h.apply(dv, dv + h.n);
@@ -1168,6 +1187,8 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
   int kd = kp.krylovdim;
   if ((long)kd > n) kd = (int)n;
   require(kd >= 1 && 6 * kd + 8 <= tevo_ctx::NSCAL, "exponentiate: krylovdim out of range");
+  require(kp.tol > 0.0 && std::isfinite(kp.tol), "exponentiate: tol must be positive and finite");
+  require(kp.maxiter >= 1, "exponentiate: maxiter must be at least 1");
   cplx* V = c->get_ws(WS_KRYLOV, (size_t)(kd + 1) * n);
   double* dh1 = c->d_scal;                 // 2*(kd+1)
   double* dh2 = c->d_scal + 2 * (kd + 1);  // 2*(kd+1)
@@ -1193,7 +1214,8 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
     double nb2[2];
     download_scalars(c, dnb, 2, nb2);
     const double beta0 = std::sqrt(nb2[0]);
-    if (!(beta0 > 0.0)) {
+    if (!std::isfinite(beta0)) throw TevoError(TEVO_EINVAL, "exponentiate: the input vector is not finite");
+    if (beta0 == 0.0) {  // exp(tA) 0 = 0
       info.converged = 1;
       return info;
     }
@@ -1247,9 +1269,13 @@ static tevo_krylov_info krylov_expv(const Heff& h, std::complex<double> t, cplx*
       if (nb > 0.0) zscal(c->stream, n, mk(1.0 / nb, 0.0), r);
     }
     if (!done_sub) {
-      while (true) {
+      // largest sub-step the full Krylov space supports (KrylovKit: dtau *= (eta/eps)^(1/krylovdim)); bounded, and a
+      // non-finite estimate is an error instead of an endless loop
+      for (int it = 0;; ++it) {
         const double eps = estimate(k, dtau, nb);
+        if (!std::isfinite(eps)) throw TevoError(TEVO_ENOTCONVERGED, "exponentiate: non-finite error estimate");
         if (eps < eta || info.numiter == kp.maxiter) break;
+        if (it >= 200 || !(dtau > 1e-300)) throw TevoError(TEVO_ENOTCONVERGED, "exponentiate did not converge");
         dtau = dtau * std::pow(eta / eps, 1.0 / kd);
       }
     }
@@ -1297,8 +1323,7 @@ extern "C" int tevo_tdvp_twosite(tevo_env* env, tevo_mps* psi, int b, tevo_compl
   require(b >= 0 && b < psi->N - 1, "tevo_tdvp_twosite: bond out of range");
   tevo_ctx* c = env->ctx;
   env_position(env, psi, b, 2);  // src/tdvp.jl:58-59
-  cplx* blk = (cplx*)((unsigned char*)c->small(1 << 17) + (1 << 16));
-  Heff h = make_heff(env, psi, b, 2, blk);
+  Heff h = make_heff(env, psi, b, 2);
   cplx* w = c->get_ws(WS_W, (size_t)h.n);
   {
     const int d = psi->d, m = psi->chi[b] * d, k = psi->chi[b + 1], n = d * psi->chi[b + 2];
@@ -1319,8 +1344,7 @@ extern "C" int tevo_tdvp_onesite(tevo_env* env, tevo_mps* psi, int i, tevo_compl
   require(i >= 0 && i < psi->N, "tevo_tdvp_onesite: site out of range");
   tevo_ctx* c = env->ctx;
   env_position(env, psi, i, 1);  // src/tdvp.jl:79-80
-  cplx* blk = (cplx*)((unsigned char*)c->small(1 << 17) + (1 << 16));
-  Heff h = make_heff(env, psi, i, 1, blk);
+  Heff h = make_heff(env, psi, i, 1);
   tevo_krylov_info ki = krylov_expv(h, std::complex<double>(t.re, t.im), psi->site[i].p, to_kp(kp));  // :81
   if (info) *info = ki;
   if (!ki.converged) throw TevoError(TEVO_ENOTCONVERGED, "exponentiate did not converge");  // :83
@@ -1433,6 +1457,7 @@ extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   out[2] = (double)q.n_fail;
   for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
   if (n >= 12) out[11] = g_heff_flops;
+  if (n >= 15) heig_counters(&out[12], &out[13], &out[14]);
   return TEVO_OK;
 }
 

@@ -196,8 +196,8 @@ void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, l
   typedef Tile<BM, AK> TA;
   typedef Tile<BN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
-  static std::once_flag once;
-  std::call_once(once, [&]() {
+  static PerDeviceOnce once;
+  once([&]() {
     TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_, CA, CB>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });

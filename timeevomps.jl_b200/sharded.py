@@ -85,6 +85,12 @@ class ShardedTEBD:
     # ---- one Trotter layer ----
     def apply_layer(self, gates: Sequence, **kw):
         """gates: BondGate-like objects with global bond .b and matrix .G, all on disjoint bonds."""
+        bonds = sorted(g.b for g in gates)
+        if any(b2 - b1 < 2 for b1, b2 in zip(bonds, bonds[1:])):
+            # e.g. a TEBD2Sweep layer (all bonds): the cut gate would read a ghost copy of a site that the right
+            # neighbour updates in the same layer
+            raise ValueError("ShardedTEBD.apply_layer: the gates of a layer must act on pairwise disjoint bonds "
+                             "(even/odd layers of TEBD2 / TEBD4); TEBD2Sweep cannot be sharded")
         mine = [g for g in gates if self.lo <= g.b < self.hi]
         right_cut = self.hi - 1          # bond (hi-1 | hi), owned by this rank
         left_cut = self.lo - 1           # bond (lo-1 | lo), owned by rank-1
@@ -178,6 +184,16 @@ class DeviceSegment(Segment):
                            g.ctx.h)
         _lib.check(lib.tevo_mps_mark_bform(self.psi.h, 1), g.ctx.h)
         self.ctx.synchronize()
+
+    @classmethod
+    def random(cls, N: int, chi: int, lo: int, hi: int, ghost: bool, seed: int = 0, d: int = 2):
+        """The segment [lo, hi) (+ ghost site) of the random saturated benchmark chain (tevo_mps_random with the same
+        seed on every rank, brought to B-form); the full chain is dropped again once the segment has been copied."""
+        from .mps import MPS
+        glob = MPS.random(N, chi, d=d, seed=seed).to_bform()
+        seg = cls(glob, lo, hi, ghost)
+        del glob
+        return seg
 
     def sync(self):
         import torch

@@ -225,6 +225,9 @@ def apply_gates_parallel(psi: MPS, Gs: Sequence[BondGate], **kw):
 def tebd_parallel(psi: MPS, H, dt, tf, alg: Optional[TEBDalg] = None, **kw) -> MPS:
     """The schedule of tebd! (bunched half steps, no callbacks) driving layer-parallel updates of a B-form state."""
     alg = TEBD2() if alg is None else alg
+    if isinstance(alg, TEBD2Sweep):
+        raise ValueError("tebd_parallel: TEBD2Sweep layers contain adjacent bonds and are not layer-parallel; "
+                         "use tebd() (sequential) for TEBD2Sweep")
     if isinstance(H, BondOperator):
         H = gates(H)
     nsteps = _nsteps(tf, dt)
