@@ -10,7 +10,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-SIGMA2_ATOL = 2e-13   # absolute floor on sigma^2 (sum of all sigma^2 = 1)
+SIGMA2_ATOL = 1e-15   # absolute floor on sigma^2 (sum of all sigma^2 = 1); measured on the B200: max rel dev 5.2e-11 over
+#                       kept weights from 2e-2 down to 1e-9, max abs dev 1.4e-16 (profiles/r02_scale_parity_tests.log)
 
 
 def _to_dev(tevo, opsi):
