@@ -202,6 +202,19 @@ int tevo_test_heig(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_de
 int tevo_test_heig_ctas(tevo_ctx* ctx, int n, const tevo_complex* A, double* evals_desc, tevo_complex* U,
                         int max_ctas);
 
+/* the two-stage tridiagonalisation (dense -> band of width 8 -> tridiagonal) stage by stage on host buffers:
+ * band_out (16 x n, column-major: B(c+d, c) at [d + 16 c]), v_out (n x n Householder vectors of stage 1), taus_out (n),
+ * d_out (n) / e_out (n-1) the tridiagonal matrix, and optionally x_out (n x k) = Q2 * x_real (n x k real) */
+int tevo_test_sbr(tevo_ctx* ctx, int n, const tevo_complex* A, tevo_complex* band_out, tevo_complex* v_out,
+                  tevo_complex* taus_out, double* d_out, double* e_out, int k, const double* x_real, tevo_complex* x_out);
+/* Hermitian eigensolver variant used by the split: 0 = two-stage reduction where it applies (default), 1 = one-stage
+ * blocked Householder reduction (kept for n > 2056 and for A/B tests); process-wide */
+int tevo_debug_set_heig_mode(int mode);
+/* cumulative counters (development / bench.py): out[0..2] CholeskyQR single / two-pass / eigen-fallback centre moves,
+ * [3..10] pivot-ratio histogram, [11] H_eff flops, [12..14] one-stage tridiagonalisation: factorisations, algorithmic
+ * bytes, panel launches, [15..16] two-stage: factorisations, algorithmic bytes of the stage-1 passes */
+int tevo_debug_counters(tevo_ctx* ctx, double* out, int n);
+
 /* per-phase device timing with CUDA events on the library stream (bench.py's roofline object).  Off by default. */
 int tevo_profile_enable(int on);
 int tevo_profile_read(char* buf, size_t cap, int reset);

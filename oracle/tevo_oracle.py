@@ -799,17 +799,31 @@ def _small_exp_col(Hk: np.ndarray, c, ishermitian: bool):
     return f
 
 
+def _signif(x: float, digits: int) -> float:
+    """Julia's round(x, sigdigits=digits) as used by KrylovKit's step control."""
+    if x == 0 or not math.isfinite(x):
+        return x
+    return float("%.*e" % (digits - 1, x))
+
+
 def exponentiate(Aop: Callable[[np.ndarray], np.ndarray], t, v0: np.ndarray, *, ishermitian=True,
-                 tol=1e-12, krylovdim=30, maxiter=100) -> Tuple[np.ndarray, KrylovInfo]:
+                 tol=1e-12, krylovdim=30, maxiter=100, mode: str = "early") -> Tuple[np.ndarray, KrylovInfo]:
     """exp(t*A) v0 by restarted Lanczos (Hermitian) / Arnoldi with full re-orthogonalisation.
 
     KrylovKit 0.4 semantics kept: ``tol`` is an error per unit time; the a-posteriori estimate is
     eps = normres * (2|e1|/3 + |e2|/6) with e_x = [exp(sgn*x*dtau*H_K)]_{K,1} (x = 1/2, 1); if it is
     not met at ``krylovdim`` the sub-step is shrunk by (tol/eps)^(1/krylovdim) and the iteration
     restarts from the advanced vector (<= maxiter restarts); ``converged`` = 1 iff the whole interval
-    was integrated.  Unlike KrylovKit this restatement also tests the estimate before the space is
-    full (same answer to within tol, fewer operator applications); the CUDA path does the same.
+    was integrated.  mode="early" (default; what the CUDA path does): the estimate is also tested before
+    the space is full (same answer to within tol, fewer operator applications).  mode="krylovkit": the
+    literal KrylovKit 0.4.0 control flow (src/matrixfun/exponentiate.jl of the pinned dependency,
+    benchmarks/Manifest.toml:58-62): the space is expanded while normres > tol and dim < krylovdim, the
+    estimate is evaluated only then, a failing step is shrunk to signif(0.9 (tol/eps)^(1/krylovdim) dtau, 2).
+    tests/test_oracle_reference_tests.py shows both modes give the same vector to within tol.
     """
+    if mode not in ("early", "krylovkit"):
+        raise ValueError(mode)
+    literal = mode == "krylovkit"
     shape = v0.shape
     v = v0.reshape(-1).astype(complex)
     n = v.size
@@ -854,8 +868,14 @@ def exponentiate(Aop: Callable[[np.ndarray], np.ndarray], t, v0: np.ndarray, *, 
             e1 = f(sgn * dtau / 2)[-1]
             e2 = f(sgn * dtau)[-1]
             eps = nb * (2 * abs(e1) / 3 + abs(e2) / 6)
-            if eps < eta or k == n:
+            if literal:
+                # KrylovKit: `while normres(fact) > eta && length(fact) < krylovdim; expand!` - no estimate yet
+                if not (nb > eta and k < kd):
+                    break
+            elif eps < eta or k == n:
                 done_sub = True
+                break
+            if k == n:
                 break
             V[k] = r / nb
         if not done_sub:
@@ -866,7 +886,10 @@ def exponentiate(Aop: Callable[[np.ndarray], np.ndarray], t, v0: np.ndarray, *, 
                 eps = nb * (2 * abs(e1) / 3 + abs(e2) / 6)
                 if eps < eta or numiter == maxiter:
                     break
-                dtau = dtau * (eta / eps) ** (1.0 / kd)
+                if literal:
+                    dtau = _signif(0.9 * (eta / eps) ** (1.0 / krylovdim) * dtau, 2)
+                else:
+                    dtau = dtau * (eta / eps) ** (1.0 / kd)
         y = f(sgn * dtau)
         w = beta * (V[:k].T @ y)
         tau_done += dtau
@@ -890,8 +913,8 @@ def sweepnext(N: int):
 
 
 def tdvp(psi: MPS, W: Sequence[np.ndarray], dt, tf, *, callback=None, hermitian=True, exp_tol=1e-14,
-         krylovdim=30, maxiter=100, normalize=True, stats: Optional[dict] = None, **kw):
-    """``tdvp!`` (src/tdvp.jl:37-96)."""
+         krylovdim=30, maxiter=100, normalize=True, stats: Optional[dict] = None, krylov_mode: str = "early", **kw):
+    """``tdvp!`` (src/tdvp.jl:37-96).  krylov_mode: see exponentiate ("krylovkit" = the literal KrylovKit 0.4 flow)."""
     nsteps = _nsteps(tf, dt)
     cb = NoTEvoCallback() if callback is None else callback
     tau = 1j * dt
@@ -910,7 +933,7 @@ def tdvp(psi: MPS, W: Sequence[np.ndarray], dt, tf, *, callback=None, hermitian=
             PH.position(psi, b)
             wf = psi.theta(b)
             wf, info = exponentiate(lambda x: PH.product(b, x), -tau / 2, wf, ishermitian=hermitian,
-                                    tol=exp_tol, krylovdim=krylovdim)
+                                    tol=exp_tol, krylovdim=krylovdim, mode=krylov_mode)
             if stats is not None:
                 stats["matvec2"] = stats.get("matvec2", 0) + info.numops
             if info.converged == 0:
@@ -924,7 +947,7 @@ def tdvp(psi: MPS, W: Sequence[np.ndarray], dt, tf, *, callback=None, hermitian=
                 PH.position(psi, i)
                 new, info = exponentiate(lambda x: PH.product(i, x), tau / 2, psi.A[i],
                                          ishermitian=hermitian, tol=exp_tol, krylovdim=krylovdim,
-                                         maxiter=maxiter)
+                                         maxiter=maxiter, mode=krylov_mode)
                 if stats is not None:
                     stats["matvec1"] = stats.get("matvec1", 0) + info.numops
                 if info.converged == 0:

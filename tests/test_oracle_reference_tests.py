@@ -250,3 +250,42 @@ def test_spec_callback():
     np.testing.assert_allclose(cb.entropies[-1], o.bond_entropies(psi), rtol=1.5e-8, atol=1e-12)
     with pytest.raises(ValueError):
         o.SpecCallback(0.1, N, bonds=[0, N - 1])                     # callback.jl:114-116
+
+
+def test_exponentiate_krylovkit_literal_mode_gives_the_same_vector():
+    """The oracle (and the CUDA path) test KrylovKit's error estimate at every Krylov dimension; KrylovKit 0.4.0
+    (benchmarks/Manifest.toml:58-62) expands to the full dimension first.  Both control flows integrate the same ODE
+    to the same tolerance: the vectors agree to exp_tol, also across restarts (long times) and for the Arnoldi branch."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(0)
+    n = 300
+    M = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    H = 3.0 * (M + M.conj().T) / 2 / np.sqrt(n)
+    v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    v /= np.linalg.norm(v)
+    for t, herm, A in ((-0.05j, True, H), (-1.0j, True, H), (-6.0j, True, H), (0.3, True, H), (-0.5j, False, H + 0.1 * M / np.sqrt(n))):
+        ref = sla.expm(t * A) @ v
+        out = {}
+        for mode in ("early", "krylovkit"):
+            w, info = o.exponentiate(lambda x: A @ x, t, v, tol=1e-12, krylovdim=30, ishermitian=herm, mode=mode)
+            assert info.converged == 1
+            assert np.linalg.norm(w - ref) < 5e-11 * max(1.0, abs(t))
+            out[mode] = (w, info)
+        assert np.linalg.norm(out["early"][0] - out["krylovkit"][0]) < 5e-11 * max(1.0, abs(t))
+        assert out["early"][1].numops <= out["krylovkit"][1].numops
+
+
+def test_tdvp_krylovkit_literal_mode_same_observables():
+    """One TDVP step of the TFIM chain with both Krylov control flows: gauge-invariant results agree to 1e-10."""
+    N = 8
+    res = {}
+    for mode in ("early", "krylovkit"):
+        p = o.MPS.random(N, 6, seed=5)
+        st = {}
+        o.tdvp(p, o.tfi_mpo(N, 1.0, 0.7), 0.1, 0.2, maxdim=8, exp_tol=1e-12, krylov_mode=mode, stats=st)
+        res[mode] = (p, st)
+    a, b = res["early"][0], res["krylovkit"][0]
+    assert a.bond_dims() == b.bond_dims()
+    assert abs(abs(o.inner(a, b)) - 1.0) < 1e-10
+    np.testing.assert_allclose(o.expect_all(a, "Sz"), o.expect_all(b, "Sz"), atol=1e-10)
+    assert res["early"][1]["matvec2"] <= res["krylovkit"][1]["matvec2"]

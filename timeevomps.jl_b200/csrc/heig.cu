@@ -657,16 +657,27 @@ void heig_counters(double* calls, double* bytes, double* launches) {
   *launches = (double)g_panel_launches.load();
 }
 
+std::atomic<int> g_heig_mode{0};  // 0: two-stage reduction where it applies (default), 1: one-stage panel kernel
+void heig_set_mode(int mode) { g_heig_mode.store(mode); }
+std::atomic<long long> g_sbr_calls{0};
+std::atomic<double> g_sbr_alg_bytes{0.0};
+void sbr_counters(double* calls, double* bytes) {
+  *calls = (double)g_sbr_calls.load();
+  *bytes = g_sbr_alg_bytes.load();
+}
+
 void Heig::init() {
   int dev = 0;
   TEVO_CUDA_CHECK(cudaGetDevice(&dev));
   TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms_, cudaDevAttrMultiProcessorCount, dev));
   // [barrier counter (one 128-byte line) | acc_yv NREP*2*PW | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
   TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW)));
+  sbr_.init(num_sms_);
 }
 
 void Heig::destroy() {
   stedc_.destroy();
+  sbr_.destroy();
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
@@ -731,6 +742,27 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   static const int tail_max = tail_cluster > 0 ? tridiag_tail_max_m(tail_cluster) : 0;
   int tail_t0 = -1;
   int p0 = 0;
+  // default: two-stage reduction (sbr.cu); TEVO_HEIG_ONESTAGE=1 selects the one-stage panel kernel below
+  static const bool force_one_stage = getenv("TEVO_HEIG_ONESTAGE") != nullptr;
+  two_stage_ = !force_one_stage && g_heig_mode.load() == 0 && n >= 2 && n <= SBR_MAX_N;
+  if (two_stage_) {
+    {
+      ProfScope ps(st, P_SBR_STAGE1);
+      sbr_.reduce_to_band(st, n, A, lda, taus_, max_ctas_);
+    }
+    {
+      ProfScope ps(st, P_SBR_CHASE);
+      sbr_.chase(st, n, d_, e_);
+    }
+    g_sbr_calls.fetch_add(1, std::memory_order_relaxed);
+    double by = 0.0;
+    for (int j = 0; j + SBR_BAND <= n - 2; j += SBR_BAND) by += 32.0 * (double)(n - j - SBR_BAND) * (double)(n - j - SBR_BAND);
+    double cur = g_sbr_alg_bytes.load(std::memory_order_relaxed);
+    while (!g_sbr_alg_bytes.compare_exchange_weak(cur, cur + by, std::memory_order_relaxed)) {
+    }
+    tail_t0 = 0;  // V^H V of every 64-column panel by GEMM below
+    p0 = n;       // skip the one-stage loop
+  }
   while (p0 < n - 1) {
     if (tail_max > 0 && n - p0 <= tail_max && n - p0 >= 2) {
       ProfScope ps(st, P_TRI_PANEL);
@@ -801,8 +833,10 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     }
     p0 = q0;
   }
-  last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
-  TEVO_LAUNCHED();
+  if (!two_stage_) {
+    last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
+    TEVO_LAUNCHED();
+  }
   if (tail_t0 >= 0) {
     // the tail kernel keeps no panel dots: V^H V of its panels (the input of the compact-WY factors) by GEMM
     const cplx ONE1 = mk(1, 0), ZERO1 = mk(0, 0);
@@ -860,7 +894,10 @@ void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ld
   if (k < 1) return;
   ProfScope ps(st, P_BACK);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
-  {
+  if (two_stage_) {
+    ProfScope ps2(st, P_SBR_Q2);
+    sbr_.apply_q2(st, n, k, Z_, n, perm_dev, U, ldu);
+  } else {
     const long total = (long)n * k;
     int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
     gather_real_cols_kernel<<<blocks, 256, 0, st>>>(n, k, Z_, n, perm_dev, U, ldu);

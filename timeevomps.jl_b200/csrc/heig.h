@@ -1,6 +1,7 @@
 // Hermitian eigensolver (device): see heig.cu.
 #pragma once
 #include "common.cuh"
+#include "sbr.h"
 #include "stedc.h"
 
 namespace tevo {
@@ -11,6 +12,11 @@ void tridiag_tail(cudaStream_t st, int cluster, int n, int t0, cplx* A, long lda
 
 // cumulative counters of the tridiagonalisation panels (process-wide): see heig.cu
 void heig_counters(double* calls, double* bytes, double* launches);
+// two-stage path: factorisations and algorithmic bytes of the stage-1 passes (read + write of the trailing matrix per
+// block of 8 columns)
+void sbr_counters(double* calls, double* bytes);
+// 0: two-stage reduction where it applies (default); 1: one-stage blocked Householder reduction (tests, A/B timing)
+void heig_set_mode(int mode);
 
 class Heig {
  public:
@@ -29,6 +35,8 @@ class Heig {
  private:
   void ensure(int n);
   Stedc stedc_;
+  Sbr sbr_;                // two-stage reduction (dense -> band -> tridiagonal), the default for n <= SBR_MAX_N
+  bool two_stage_ = false;  // which reduction produced the current factorisation
   int num_sms_ = 148;
   int max_ctas_ = 0;
   int cap_ = 0, n_ = 0;

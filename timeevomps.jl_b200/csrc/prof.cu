@@ -10,7 +10,8 @@ thread_local bool tl_prof_thread = true;
 static const char* kNames[P_COUNT] = {"theta_gemm", "gate_apply", "rho_gemm",  "tridiag_panel", "tridiag_her2k", "tridiag_wy",
                                       "stedc",      "backtransform", "split_gemm", "residual",    "truncate",      "hop_gemm",
                                       "heff_apply", "krylov_blas1",  "env_update", "measure",
-                                      "cholqr_gram", "cholqr_factor", "cholqr_inverse", "cholqr_q"};
+                                      "cholqr_gram", "cholqr_factor", "cholqr_inverse", "cholqr_q",
+                                      "sbr_stage1", "sbr_chase", "sbr_q2"};
 
 cudaEvent_t Prof::get() {
   if (!pool.empty()) {

@@ -28,6 +28,9 @@ enum ProfId {
   P_CHOL_FACTOR,    // CholeskyQR: blocked Cholesky (diagonal blocks + panel/trailing GEMMs)
   P_CHOL_INV,       // CholeskyQR: triangular inverse assembly
   P_CHOL_Q,         // CholeskyQR: Q = A L^-H
+  P_SBR_STAGE1,     // two-stage tridiagonalisation: dense -> band (persistent kernel)
+  P_SBR_CHASE,      // two-stage tridiagonalisation: band -> tridiagonal (bulge chasing)
+  P_SBR_Q2,         // back-transformation with the stage-2 reflectors
   P_COUNT
 };
 

@@ -60,6 +60,420 @@ __device__ inline void larfg(cplx alpha, double xn2, double& beta, cplx& tau, cp
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// stage 1: dense -> band (width 8).  Persistent cooperative kernel, 256 threads per CTA, one CTA per SM.
+// ------------------------------------------------------------------------------------------------------------------
+struct S1Args {
+  int n;
+  cplx* A;
+  long lda;
+  cplx* Bd;       // band out (lower storage, LDB diagonals per column)
+  cplx* taus;     // n
+  cplx* Vb;       // [2][bstride]: reflectors of the block, row-major (row r: 8 entries), rows >= j+8 valid
+  cplx* Wb;       // [2][bstride]: W of the block
+  double* Yb;     // [2][2*bstride]: Y = A V accumulators (re, im)
+  double* small;  // [2][256]: S = V^H Y accumulator (8x8 complex) followed by the T factor (8x8 complex)
+  unsigned* bar;  // grid barrier counter (zeroed before the launch)
+  long bstride;   // (n + 64) * 8
+};
+
+__device__ inline void grid_bar(unsigned* ctr, unsigned epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    const unsigned target = epoch * gridDim.x;
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// sum of NV doubles over the CTA (256 threads); result in all threads.  red: >= NV*8 doubles of shared memory
+template <int NV>
+__device__ inline void cta_sum(double (&v)[NV], double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * 8 + wid] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x += red[i * 8 + w];
+    v[i] = x;
+  }
+}
+
+// operand rows of one 64-column tile in shared memory: entry (c, q) at c*8 + q + (c >> 4): the four column groups of a
+// warp (16 columns apart) fall into different banks
+constexpr int OPS = 64 * 8 + 4;
+__device__ inline int opi(int c, int q) { return c * 8 + q + (c >> 4); }
+
+// Householder QR of the sub-band panel of block bi (columns j .. j+7, rows j+8 .. n-1) by one CTA; the panel lives in
+// registers (thread t holds the panel rows t, t+256, ...).  Writes the band entries of the 8 columns, the reflectors
+// (explicit form) to Vb[p] and into A, their scalars, and the compact-WY T factor.
+__device__ __noinline__ void panel_qr(const S1Args& a, int j, int p, double* red, cplx* sbc, cplx* sTq) {
+  const int n = a.n, t = threadIdx.x;
+  const int m = n - j - SB;
+  const int bw = min(SB, m - 1);
+  cplx P[8][SB];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int ir = t + 256 * u;
+#pragma unroll
+    for (int c = 0; c < SB; ++c) P[u][c] = (ir < m) ? ldcg_c(a.A + (long)(j + c) * a.lda + (j + SB + ir)) : mk(0, 0);
+  }
+  if (t < 64) {  // diagonal block -> band
+    const int rr = t & 7, cc = t >> 3;
+    if (rr >= cc) {
+      cplx x = ldcg_c(a.A + (long)(j + cc) * a.lda + (j + rr));
+      if (rr == cc) x.y = 0.0;
+      a.Bd[(long)LDB * (j + cc) + (rr - cc)] = x;
+    }
+  }
+  cplx tauv[SB];
+  double betav[SB];
+  // sTq: T factor, row pr written by thread pr only (T(pr, q) = -tau_q sum_l T(pr, l) G(l, q), G = V^H V)
+  if (t < 64) sTq[t] = mk(0, 0);
+#pragma unroll
+  for (int ic = 0; ic < SB; ++ic) {
+    tauv[ic] = mk(0, 0);
+    betav[ic] = 0.0;
+    if (ic < bw) {
+      double part[1] = {0.0};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ir = t + 256 * u;
+        if (ir > ic) part[0] += cabs2(P[u][ic]);
+      }
+      if (t == ic) sbc[0] = P[0][ic];
+      cta_sum<1>(part, red);
+      const cplx alpha = sbc[0];
+      double beta;
+      cplx tau, scal;
+      larfg(alpha, part[0], beta, tau, scal);
+      tauv[ic] = tau;
+      betav[ic] = beta;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ir = t + 256 * u;
+        if (ir > ic)
+          P[u][ic] = cmul(P[u][ic], scal);
+        else if (ir == ic)
+          P[u][ic] = mk(1, 0);
+      }
+      // one reduction of 7 complex numbers: slots c-1 (c > ic): w_c = v^H P(:, c) for the panel update;
+      // slots pc (pc < ic): G(pc, ic) = v_pc^H v_ic for the T factor
+      double ws[2 * (SB - 1)];
+#pragma unroll
+      for (int x = 0; x < 2 * (SB - 1); ++x) ws[x] = 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ir = t + 256 * u;
+        if (ir >= ic) {
+          const cplx v = P[u][ic];
+#pragma unroll
+          for (int c = ic + 1; c < SB; ++c) {
+            const cplx x = P[u][c];
+            ws[2 * (c - 1)] += v.x * x.x + v.y * x.y;
+            ws[2 * (c - 1) + 1] += v.x * x.y - v.y * x.x;
+          }
+#pragma unroll
+          for (int pc = 0; pc < ic; ++pc) {
+            const cplx x = P[u][pc];  // ir >= ic > pc: below the unit of column pc
+            ws[2 * pc] += x.x * v.x + x.y * v.y;
+            ws[2 * pc + 1] += x.x * v.y - x.y * v.x;
+          }
+        }
+      }
+      cta_sum<2 * (SB - 1)>(ws, red);
+      const cplx ct = cconj(tau);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int ir = t + 256 * u;
+        if (ir >= ic) {
+#pragma unroll
+          for (int c = ic + 1; c < SB; ++c) cfms(P[u][c], cmul(ct, P[u][ic]), mk(ws[2 * (c - 1)], ws[2 * (c - 1) + 1]));
+        }
+      }
+      if (t < ic) {
+        cplx acc = mk(0, 0);
+#pragma unroll
+        for (int l = 0; l < ic; ++l)
+          if (l >= t) cfma(acc, sTq[t + SB * l], mk(ws[2 * l], ws[2 * l + 1]));
+        sTq[t + SB * ic] = cmul(mk(-tau.x, -tau.y), acc);
+      } else if (t == ic) {
+        sTq[t + SB * ic] = tau;
+      }
+    }
+  }
+  __syncthreads();
+  if (t < 64) reinterpret_cast<cplx*>(a.small + 256 * p + 128)[t] = sTq[t];
+  if (t < SB) a.taus[j + t] = mk(0, 0);
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < SB; ++c)
+    if (t == 0) a.taus[j + c] = tauv[c];
+  // band entries of the R factor (rows j+8+ir, ir <= c) and explicit reflectors
+  cplx* Vp = a.Vb + (long)p * a.bstride;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int ir = t + 256 * u;
+    if (ir < m) {
+#pragma unroll
+      for (int c = 0; c < SB; ++c) {
+        if (ir <= c) {
+          cplx x = P[u][c];
+          if (ir == c && c < bw) x = mk(betav[c], 0);
+          a.Bd[(long)LDB * (j + c) + (SB + ir - c)] = x;
+        }
+        cplx v = mk(0, 0);
+        if (c < bw) v = (ir < c) ? mk(0, 0) : ((ir == c) ? mk(1, 0) : P[u][c]);
+        Vp[(long)(j + SB + ir) * SB + c] = v;
+        a.A[(long)(j + c) * a.lda + (j + SB + ir)] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
+  __shared__ double red[14 * 8];
+  __shared__ cplx sbc[4];
+  __shared__ cplx sT[64], sS[64], sX[64], sM[64];
+  __shared__ cplx sWc[9 * 8], sVc[9 * 8];
+  __shared__ cplx sOp[3][OPS];
+  __shared__ cplx sSp[8][64];
+  const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x;
+  const int NB = (n >= SB + 2) ? (n - 2 - SB) / SB + 1 : 0;  // blocks j = 8 bi with j + 8 <= n - 2
+  unsigned epoch = 0;
+  for (int bi = 0; bi <= NB; ++bi) {
+    const int j = SB * bi;
+    const int p = bi & 1, pp = p ^ 1;
+    const int ncol = (bi < NB) ? SB : n - j;  // <= 9
+    // ---------------- (1) W of block bi-1, its update applied to columns j .. j+ncol-1 (rows j .. n-1) ----------------
+    if (bi > 0) {
+      const cplx* Vq = a.Vb + (long)pp * a.bstride;
+      cplx* Wq = a.Wb + (long)pp * a.bstride;
+      const cplx* Yq = reinterpret_cast<const cplx*>(a.Yb + 2 * (long)pp * a.bstride);
+      const cplx* Sg = reinterpret_cast<const cplx*>(a.small + 256 * pp);
+      const cplx* Tg = Sg + 64;
+      if (tid < 64) {
+        sS[tid] = ldcg_c(Sg + tid);
+        sT[tid] = ldcg_c(Tg + tid);
+      }
+      __syncthreads();
+      if (tid < 64) {  // X = S T
+        const int x = tid & 7, y = tid >> 3;
+        cplx acc = mk(0, 0);
+#pragma unroll
+        for (int l = 0; l < SB; ++l) cfma(acc, sS[x + SB * l], sT[l + SB * y]);
+        sX[tid] = acc;
+      }
+      __syncthreads();
+      if (tid < 64) {  // M = 1/2 T^H X
+        const int x = tid & 7, y = tid >> 3;
+        cplx acc = mk(0, 0);
+#pragma unroll
+        for (int l = 0; l < SB; ++l) cfma_conj(acc, sT[l + SB * x], sX[l + SB * y]);
+        sM[tid] = cscale(0.5, acc);
+      }
+      __syncthreads();
+      if (tid < ncol * SB) {  // W and V of the rows j .. j+ncol-1 (the columns being updated)
+        const int cc = tid >> 3, q = tid & 7;
+        const long r = j + cc;
+        cplx acc = mk(0, 0);
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          cfma(acc, ldcg_c(Yq + r * SB + l), sT[l + SB * q]);
+          cfms(acc, ldcg_c(Vq + r * SB + l), sM[l + SB * q]);
+        }
+        sWc[tid] = acc;
+        sVc[tid] = ldcg_c(Vq + r * SB + q);
+      }
+      __syncthreads();
+      const int q = lane & 7, sub = lane >> 3;
+      for (long rb = j + (long)blockIdx.x * 32 + warp * 4; rb < n; rb += 32L * G) {
+        // the loop bound is warp-uniform (the shuffles below need all lanes); rows past the end are inactive
+        const long r = rb + sub;
+        const bool act = r < n;
+        const cplx yq = act ? ldcg_c(Yq + r * SB + q) : mk(0, 0);
+        const cplx vq = act ? ldcg_c(Vq + r * SB + q) : mk(0, 0);
+        cplx yv[SB], vv[SB];
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          yv[l] = shfl_c(yq, (lane & 24) + l);
+          vv[l] = shfl_c(vq, (lane & 24) + l);
+        }
+        cplx wq = mk(0, 0);
+#pragma unroll
+        for (int l = 0; l < SB; ++l) {
+          cfma(wq, yv[l], sT[l + SB * q]);
+          cfms(wq, vv[l], sM[l + SB * q]);
+        }
+        if (act) Wq[r * SB + q] = wq;
+        cplx wv[SB];
+#pragma unroll
+        for (int l = 0; l < SB; ++l) wv[l] = shfl_c(wq, (lane & 24) + l);
+        for (int c = q; c < ncol; c += SB) {
+          if (act) {
+            cplx* ap = a.A + (long)(j + c) * a.lda + r;
+            cplx x = ldcg_c(ap);
+#pragma unroll
+            for (int l = 0; l < SB; ++l) {
+              cfms(x, vv[l], cconj(sWc[c * SB + l]));
+              cfms(x, wv[l], cconj(sVc[c * SB + l]));
+            }
+            *ap = x;
+          }
+        }
+      }
+    }
+    // accumulators of block bi
+    {
+      double* Yz = a.Yb + 2 * (long)p * a.bstride;
+      for (long e = (long)blockIdx.x * 256 + tid; e < 2L * (n + 8) * SB; e += 256L * G) Yz[e] = 0.0;
+      if (blockIdx.x == 0 && tid < 128) a.small[256 * p + tid] = 0.0;
+    }
+    grid_bar(a.bar, ++epoch);
+    if (bi == NB) {
+      // remaining columns j .. n-1: all inside the band
+      for (int e = blockIdx.x * 256 + tid; e < ncol * ncol; e += 256 * G) {
+        const int rr = e % ncol, cc = e / ncol;
+        if (rr >= cc) {
+          cplx x = ldcg_c(a.A + (long)(j + cc) * a.lda + (j + rr));
+          if (rr == cc) x.y = 0.0;
+          a.Bd[(long)LDB * (j + cc) + (rr - cc)] = x;
+        }
+      }
+      if (blockIdx.x == 0 && tid < ncol) a.taus[j + tid] = mk(0, 0);
+      break;
+    }
+    // ---------------- (2) panel QR of block bi ----------------
+    if (blockIdx.x == 0) panel_qr(a, j, p, red, sbc, sX);
+    grid_bar(a.bar, ++epoch);
+    // ---------------- (3) one pass over A[R, R], R = j+8 .. n-1: update of block bi-1, Y = A V, S = V^H Y ----------------
+    {
+      const int r_lo = j + SB, m = n - r_lo;
+      const int nt = (m + 63) / 64;
+      const int ntiles = nt * nt;
+      const int chunk = (ntiles + G - 1) / G;
+      const int t_lo = blockIdx.x * chunk, t_hi = min(ntiles, t_lo + chunk);
+      const bool has_prev = bi > 0;
+      const cplx* Vprev = a.Vb + (long)pp * a.bstride;
+      const cplx* Wprev = a.Wb + (long)pp * a.bstride;
+      const cplx* Vnew = a.Vb + (long)p * a.bstride;
+      double* Yacc = a.Yb + 2 * (long)p * a.bstride;
+      double* Sacc = a.small + 256 * p;
+      const int rl = 8 * warp + (lane & 7);  // row inside the tile
+      const int cgp = lane >> 3;             // column group: columns 16*cgp .. 16*cgp+15 of the tile
+      cplx vp[SB], wp[SB], yacc[SB];
+      int curI = -1;
+      long r = 0;
+      auto flush = [&]() {
+        // reduce over the four column groups, add to Y, accumulate S = V^H Y over the rows of the warp
+#pragma unroll
+        for (int q = 0; q < SB; ++q) {
+          yacc[q] = cadd(yacc[q], shfl_xor_c(yacc[q], 8));
+          yacc[q] = cadd(yacc[q], shfl_xor_c(yacc[q], 16));
+        }
+        const bool own = (cgp == 0) && (r < n);
+        cplx vn[SB];
+#pragma unroll
+        for (int q = 0; q < SB; ++q) vn[q] = own ? ldcg_c(Vnew + r * SB + q) : mk(0, 0);
+        if (own) {
+#pragma unroll
+          for (int q = 0; q < SB; ++q) {
+            atomicAdd(Yacc + 2 * (r * SB + q), yacc[q].x);
+            atomicAdd(Yacc + 2 * (r * SB + q) + 1, yacc[q].y);
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < SB; ++x) {
+#pragma unroll
+          for (int y = 0; y < SB; ++y) {
+            cplx sp = mk(0, 0);
+            cfma_conj(sp, vn[x], yacc[y]);
+            sp = cadd(sp, shfl_xor_c(sp, 1));
+            sp = cadd(sp, shfl_xor_c(sp, 2));
+            sp = cadd(sp, shfl_xor_c(sp, 4));
+            if (lane == 0) sSp[warp][x + SB * y] = sp;
+          }
+        }
+        __syncthreads();
+        if (tid < 64) {
+          cplx acc = mk(0, 0);
+#pragma unroll
+          for (int w = 0; w < 8; ++w) acc = cadd(acc, sSp[w][tid]);
+          atomicAdd(Sacc + 2 * tid, acc.x);
+          atomicAdd(Sacc + 2 * tid + 1, acc.y);
+        }
+        __syncthreads();
+      };
+      for (int tI = t_lo; tI < t_hi; ++tI) {
+        const int I = tI / nt, J = tI % nt;
+        if (I != curI) {
+          if (curI >= 0) flush();
+          curI = I;
+          r = r_lo + 64L * I + rl;
+#pragma unroll
+          for (int q = 0; q < SB; ++q) {
+            yacc[q] = mk(0, 0);
+            vp[q] = (has_prev && r < n) ? ldcg_c(Vprev + r * SB + q) : mk(0, 0);
+            wp[q] = (has_prev && r < n) ? ldcg_c(Wprev + r * SB + q) : mk(0, 0);
+          }
+        }
+        const long c0 = r_lo + 64L * J;
+        __syncthreads();  // the previous tile's operand rows are no longer read
+        for (int e = tid; e < 64 * SB; e += 256) {
+          const int c = e >> 3, q = e & 7;
+          const long cg_ = c0 + c;
+          const bool in = cg_ < n;
+          sOp[0][opi(c, q)] = (in && has_prev) ? ldcg_c(Wprev + cg_ * SB + q) : mk(0, 0);
+          sOp[1][opi(c, q)] = (in && has_prev) ? ldcg_c(Vprev + cg_ * SB + q) : mk(0, 0);
+          sOp[2][opi(c, q)] = in ? ldcg_c(Vnew + cg_ * SB + q) : mk(0, 0);
+        }
+        __syncthreads();
+        cplx av[16];
+        cplx* ap = a.A + (c0 + 16 * cgp) * a.lda + r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) av[i] = (r < n && c0 + 16 * cgp + i < n) ? ldcg_c(ap + (long)i * a.lda) : mk(0, 0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = 16 * cgp + i;
+          cplx x = av[i];
+          if (has_prev) {
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+              cfms(x, vp[q], cconj(sOp[0][opi(c, q)]));
+              cfms(x, wp[q], cconj(sOp[1][opi(c, q)]));
+            }
+            if (r < n && c0 + c < n) ap[(long)i * a.lda] = x;
+          }
+#pragma unroll
+          for (int q = 0; q < SB; ++q) cfma(yacc[q], x, sOp[2][opi(c, q)]);
+        }
+      }
+      if (curI >= 0) flush();
+    }
+    grid_bar(a.bar, ++epoch);
+  }
+}
+
+// explicit zeros above the reflectors: column c of A keeps rows >= c + 8 (the back-transformation reads A as V)
+__global__ void sbr_zero_upper_kernel(int n, cplx* A, long lda) {
+  const int c = blockIdx.x;
+  const int top = (c + SB <= n - 2) ? c + SB : n;  // columns without reflector are cleared entirely
+  for (int r = threadIdx.x; r < top; r += blockDim.x) A[(long)c * lda + r] = mk(0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // stage 2: band (width 8, lower storage Bd[d + LDB*c] = B(c+d, c), d < 16) -> real symmetric tridiagonal (d, e)
 // ------------------------------------------------------------------------------------------------------------------
 // One warp per sweep s (eliminates column s below the sub-diagonal and chases the bulge to the end of the matrix).
@@ -321,6 +735,34 @@ void Sbr::ensure(int n) {
   TEVO_CUDA_CHECK(cudaMalloc(&Yb_, sizeof(cplx) * (size_t)2 * SB * (n + 64)));
   TEVO_CUDA_CHECK(cudaMalloc(&small_, sizeof(double) * SBR_SMALL_DOUBLES));
   cap_ = n;
+}
+
+void Sbr::reduce_to_band(cudaStream_t st, int n, cplx* A, long lda, cplx* taus, int max_ctas) {
+  if (n > SBR_MAX_N) throw TevoError(1, "sbr: n too large for the two-stage reduction");
+  ensure(n);
+  // band array: diagonals 0..8 written by stage 1, the bulge diagonals 9..15 start as zeros
+  TEVO_CUDA_CHECK(cudaMemsetAsync(Bd_, 0, sizeof(cplx) * (size_t)LDB * (n + 16), st));
+  TEVO_CUDA_CHECK(cudaMemsetAsync(small_, 0, sizeof(double) * SBR_SMALL_DOUBLES, st));
+  S1Args a;
+  a.n = n;
+  a.A = A;
+  a.lda = lda;
+  a.Bd = Bd_;
+  a.taus = taus;
+  a.Vb = Vb_;
+  a.Wb = Wb_;
+  a.Yb = reinterpret_cast<double*>(Yb_);
+  a.small = small_;
+  a.bar = reinterpret_cast<unsigned*>(small_ + 512);
+  a.bstride = (long)(n + 64) * SB;
+  int grid = num_sms_;
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
+  grid = std::max(1, grid);
+  void* args[] = {&a};
+  TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sbr_stage1_kernel, dim3(grid), dim3(256), args, 0, st));
+  TEVO_LAUNCHED();
+  sbr_zero_upper_kernel<<<n, 128, 0, st>>>(n, A, lda);
+  TEVO_LAUNCHED();
 }
 
 void Sbr::chase(cudaStream_t st, int n, double* d, double* e) {

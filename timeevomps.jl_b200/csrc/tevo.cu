@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "prof.h"
+#include "sbr.h"
 #include "split.h"
 #include "zgemm.h"
 
@@ -1449,6 +1450,51 @@ extern "C" int tevo_profile_read(char* buf, size_t cap, int reset) {
 }
 
 /* development counters: out[0..2] = CholQR single-pass / double-pass / failed, out[3..10] = pivot-ratio histogram */
+/* two-stage tridiagonalisation, stage by stage, on host buffers (tests / development):
+ *   band_out (16 x n, column-major): the band matrix after stage 1, B(c+d, c) at [d + 16*c], d <= 8
+ *   v_out (n x n): A after stage 1 = Householder vectors (explicit zeros / unit entries), taus_out (n)
+ *   d_out (n), e_out (n-1): the tridiagonal matrix after stage 2
+ *   x (n x k, in/out, optional): overwritten by Q2 * x_real where x_real (n x k doubles, column-major) is the input */
+extern "C" int tevo_test_sbr(tevo_ctx* ctx, int n, const tevo_complex* A, tevo_complex* band_out, tevo_complex* v_out,
+                             tevo_complex* taus_out, double* d_out, double* e_out, int k, const double* x_real,
+                             tevo_complex* x_out) {
+  TEVO_TRY(ctx)
+  require(ctx && A && n >= 2, "tevo_test_sbr: bad argument");
+  Sbr sbr;
+  int sms = 148;
+  TEVO_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  sbr.init(sms);
+  cplx* dA = ctx->get_ws(WS_T1, (size_t)n * n);
+  cplx* dt = ctx->get_ws(WS_T2, (size_t)n + 64 + (size_t)n * std::max(k, 1));
+  double* dd = reinterpret_cast<double*>(ctx->get_ws(WS_W, (size_t)2 * n + (size_t)n * std::max(k, 1)));
+  TEVO_CUDA_CHECK(cudaMemcpyAsync(dA, A, sizeof(cplx) * (size_t)n * n, cudaMemcpyHostToDevice, ctx->stream));
+  sbr.reduce_to_band(ctx->stream, n, dA, n, dt, 0);
+  if (band_out)
+    TEVO_CUDA_CHECK(cudaMemcpyAsync(band_out, sbr.band(), sizeof(cplx) * (size_t)SBR_LDB * n, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+  if (v_out) TEVO_CUDA_CHECK(cudaMemcpyAsync(v_out, dA, sizeof(cplx) * (size_t)n * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (taus_out) TEVO_CUDA_CHECK(cudaMemcpyAsync(taus_out, dt, sizeof(cplx) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  TEVO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  sbr.chase(ctx->stream, n, dd, dd + n);
+  if (d_out) TEVO_CUDA_CHECK(cudaMemcpyAsync(d_out, dd, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (e_out) TEVO_CUDA_CHECK(cudaMemcpyAsync(e_out, dd + n, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (k > 0 && x_real && x_out) {
+    double* dz = dd + 2 * n;
+    cplx* dx = dt + n + 64;
+    TEVO_CUDA_CHECK(cudaMemcpyAsync(dz, x_real, sizeof(double) * (size_t)n * k, cudaMemcpyHostToDevice, ctx->stream));
+    sbr.apply_q2(ctx->stream, n, k, dz, n, nullptr, dx, n);
+    TEVO_CUDA_CHECK(cudaMemcpyAsync(x_out, dx, sizeof(cplx) * (size_t)n * k, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TEVO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  sbr.destroy();
+  TEVO_CATCH
+}
+
+extern "C" int tevo_debug_set_heig_mode(int mode) {
+  heig_set_mode(mode);
+  return TEVO_OK;
+}
+
 extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   if (!ctx || !out || n < 11) return TEVO_EINVAL;
   CholQR& q = ctx->split.cholqr();
@@ -1458,6 +1504,7 @@ extern "C" int tevo_debug_counters(tevo_ctx* ctx, double* out, int n) {
   for (int i = 0; i < 8; ++i) out[3 + i] = q.ratio_hist[i];
   if (n >= 12) out[11] = g_heff_flops;
   if (n >= 15) heig_counters(&out[12], &out[13], &out[14]);
+  if (n >= 17) sbr_counters(&out[15], &out[16]);
   return TEVO_OK;
 }
 
