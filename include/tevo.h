@@ -207,8 +207,9 @@ int tevo_test_heig_ctas(tevo_ctx* ctx, int n, const tevo_complex* A, double* eva
  * d_out (n) / e_out (n-1) the tridiagonal matrix, and optionally x_out (n x k) = Q2 * x_real (n x k real) */
 int tevo_test_sbr(tevo_ctx* ctx, int n, const tevo_complex* A, tevo_complex* band_out, tevo_complex* v_out,
                   tevo_complex* taus_out, double* d_out, double* e_out, int k, const double* x_real, tevo_complex* x_out);
-/* Hermitian eigensolver variant used by the split: 0 = two-stage reduction where it applies (default), 1 = one-stage
- * blocked Householder reduction (kept for n > 2056 and for A/B tests); process-wide */
+/* Hermitian eigensolver variant used by the split (process-wide): 0 = default (one-stage blocked Householder
+ * reduction; the two-stage one if the environment sets TEVO_HEIG_TWOSTAGE), 1 = one-stage, 2 = two-stage reduction
+ * dense -> band of width 8 -> tridiagonal (n <= 2056; parity-tested, not yet faster: DESIGN.md) */
 int tevo_debug_set_heig_mode(int mode);
 /* cumulative counters (development / bench.py): out[0..2] CholeskyQR single / two-pass / eigen-fallback centre moves,
  * [3..10] pivot-ratio histogram, [11] H_eff flops, [12..14] one-stage tridiagonalisation: factorisations, algorithmic

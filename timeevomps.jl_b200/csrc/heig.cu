@@ -657,7 +657,7 @@ void heig_counters(double* calls, double* bytes, double* launches) {
   *launches = (double)g_panel_launches.load();
 }
 
-std::atomic<int> g_heig_mode{0};  // 0: two-stage reduction where it applies (default), 1: one-stage panel kernel
+std::atomic<int> g_heig_mode{0};  // 0: default (one-stage unless TEVO_HEIG_TWOSTAGE is set), 1: one-stage, 2: two-stage
 void heig_set_mode(int mode) { g_heig_mode.store(mode); }
 std::atomic<long long> g_sbr_calls{0};
 std::atomic<double> g_sbr_alg_bytes{0.0};
@@ -742,9 +742,11 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   static const int tail_max = tail_cluster > 0 ? tridiag_tail_max_m(tail_cluster) : 0;
   int tail_t0 = -1;
   int p0 = 0;
-  // default: two-stage reduction (sbr.cu); TEVO_HEIG_ONESTAGE=1 selects the one-stage panel kernel below
-  static const bool force_one_stage = getenv("TEVO_HEIG_ONESTAGE") != nullptr;
-  two_stage_ = !force_one_stage && g_heig_mode.load() == 0 && n >= 2 && n <= SBR_MAX_N;
+  // default: the one-stage panel kernel below.  The two-stage reduction (sbr.cu: dense -> band of width 8 ->
+  // tridiagonal) is parity-green but not yet faster: TEVO_HEIG_TWOSTAGE=1 or
+  // tevo_debug_set_heig_mode(2) selects it.
+  static const bool env_two_stage = getenv("TEVO_HEIG_TWOSTAGE") != nullptr;
+  two_stage_ = (env_two_stage || g_heig_mode.load() == 2) && g_heig_mode.load() != 1 && n >= 2 && n <= SBR_MAX_N;
   if (two_stage_) {
     {
       ProfScope ps(st, P_SBR_STAGE1);

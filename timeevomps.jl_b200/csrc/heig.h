@@ -15,7 +15,8 @@ void heig_counters(double* calls, double* bytes, double* launches);
 // two-stage path: factorisations and algorithmic bytes of the stage-1 passes (read + write of the trailing matrix per
 // block of 8 columns)
 void sbr_counters(double* calls, double* bytes);
-// 0: two-stage reduction where it applies (default); 1: one-stage blocked Householder reduction (tests, A/B timing)
+// 0: default (one-stage; two-stage if TEVO_HEIG_TWOSTAGE is set); 1: one-stage blocked Householder reduction;
+// 2: two-stage reduction dense -> band -> tridiagonal where it applies (n <= SBR_MAX_N)
 void heig_set_mode(int mode);
 
 class Heig {
@@ -35,7 +36,7 @@ class Heig {
  private:
   void ensure(int n);
   Stedc stedc_;
-  Sbr sbr_;                // two-stage reduction (dense -> band -> tridiagonal), the default for n <= SBR_MAX_N
+  Sbr sbr_;                // two-stage reduction (dense -> band -> tridiagonal), opt-in (see factor())
   bool two_stage_ = false;  // which reduction produced the current factorisation
   int num_sms_ = 148;
   int max_ctas_ = 0;

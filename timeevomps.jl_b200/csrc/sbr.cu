@@ -60,8 +60,22 @@ __device__ inline void larfg(cplx alpha, double xn2, double& beta, cplx& tau, cp
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// stage 1: dense -> band (width 8).  Persistent cooperative kernel, 256 threads per CTA, one CTA per SM.
+// stage 1: dense -> band (width 8).  Persistent cooperative kernel, 512 threads per CTA, one CTA per SM.
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef TEVO_SBR_TIMING
+__device__ unsigned long long g_sbr_cycles[16];
+#define ST_MARK(slot)                                                    \
+  do {                                                                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
+      long long _now = clock64();                                        \
+      atomicAdd(&g_sbr_cycles[slot], (unsigned long long)(_now - _t0));  \
+      _t0 = _now;                                                        \
+    }                                                                    \
+  } while (0)
+#else
+#define ST_MARK(slot)
+#endif
+
 struct S1Args {
   int n;
   cplx* A;
@@ -89,7 +103,11 @@ __device__ inline void grid_bar(unsigned* ctr, unsigned epoch) {
   __syncthreads();
 }
 
-// sum of NV doubles over the CTA (256 threads); result in all threads.  red: >= NV*8 doubles of shared memory
+constexpr int S1_NT = 512;          // threads per CTA of the stage-1 kernel
+constexpr int S1_NW = S1_NT / 32;   // warps
+constexpr int S1_RPT = 4;           // panel rows per thread in the QR (SBR_MAX_N - 8 <= S1_NT * S1_RPT)
+
+// sum of NV doubles over the CTA; result in all threads.  red: >= NV*S1_NW doubles of shared memory
 template <int NV>
 __device__ inline void cta_sum(double (&v)[NV], double* red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -98,14 +116,14 @@ __device__ inline void cta_sum(double (&v)[NV], double* red) {
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) red[i * 8 + wid] = v[i];
+    for (int i = 0; i < NV; ++i) red[i * S1_NW + wid] = v[i];
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     double x = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) x += red[i * 8 + w];
+    for (int w = 0; w < S1_NW; ++w) x += red[i * S1_NW + w];
     v[i] = x;
   }
 }
@@ -115,19 +133,113 @@ __device__ inline void cta_sum(double (&v)[NV], double* red) {
 constexpr int OPS = 64 * 8 + 4;
 __device__ inline int opi(int c, int q) { return c * 8 + q + (c >> 4); }
 
-// Householder QR of the sub-band panel of block bi (columns j .. j+7, rows j+8 .. n-1) by one CTA; the panel lives in
-// registers (thread t holds the panel rows t, t+256, ...).  Writes the band entries of the 8 columns, the reflectors
+// Householder QR of the sub-band panel of block bi (columns j .. j+7, rows j+8 .. n-1) by one CTA.  Thread t owns the
+// panel rows t, t+512, ...: columns 0..3 of its rows live in registers, columns 4..7 in shared memory (sP, private to
+// the thread, so no synchronisation is needed for it).  Writes the band entries of the 8 columns, the reflectors
 // (explicit form) to Vb[p] and into A, their scalars, and the compact-WY T factor.
-__device__ __noinline__ void panel_qr(const S1Args& a, int j, int p, double* red, cplx* sbc, cplx* sTq) {
+constexpr int QR_MP = SBR_MAX_N;  // row stride of the shared-memory half of the panel
+#define PGET(u, c) (((c) < 4) ? PR[u][(c)&3] : sP[((c)-4) * QR_MP + t + S1_NT * (u)])
+#define PSET(u, c, val)                              \
+  do {                                               \
+    if ((c) < 4)                                     \
+      PR[u][(c)&3] = (val);                          \
+    else                                             \
+      sP[((c)-4) * QR_MP + t + S1_NT * (u)] = (val); \
+  } while (0)
+
+// one column of the panel QR (IC is a compile-time constant so that every access to PR has a static index and the
+// register half of the panel really stays in registers)
+template <int IC>
+__device__ __forceinline__ void qr_column(cplx (&PR)[S1_RPT][4], cplx* sP, int t, int bw, cplx (&tauv)[SB], double (&betav)[SB],
+                                          double* red, cplx* sbc, cplx* sTq) {
+  tauv[IC] = mk(0, 0);
+  betav[IC] = 0.0;
+  if (IC >= bw) return;
+  double part[1] = {0.0};
+#pragma unroll
+  for (int u = 0; u < S1_RPT; ++u) {
+    const int ir = t + S1_NT * u;
+    if (ir > IC) part[0] += cabs2(PGET(u, IC));
+  }
+  if (t == IC) sbc[0] = PGET(0, IC);
+  cta_sum<1>(part, red);
+  const cplx alpha = sbc[0];
+  double beta;
+  cplx tau, scal;
+  larfg(alpha, part[0], beta, tau, scal);
+  tauv[IC] = tau;
+  betav[IC] = beta;
+  cplx vcol[S1_RPT];  // the reflector entries of the own rows (0 above the unit, 1 at the unit)
+#pragma unroll
+  for (int u = 0; u < S1_RPT; ++u) {
+    const int ir = t + S1_NT * u;
+    cplx x = PGET(u, IC);
+    if (ir > IC) {
+      x = cmul(x, scal);
+      PSET(u, IC, x);
+    } else if (ir == IC) {
+      x = mk(1, 0);
+      PSET(u, IC, x);
+    }
+    vcol[u] = (ir >= IC) ? x : mk(0, 0);
+  }
+  // one reduction of 7 complex numbers: slots c-1 (c > IC): w_c = v^H P(:, c) for the panel update;
+  // slots pc (pc < IC): G(pc, IC) = v_pc^H v_IC for the T factor
+  double ws[2 * (SB - 1)];
+#pragma unroll
+  for (int x = 0; x < 2 * (SB - 1); ++x) ws[x] = 0.0;
+#pragma unroll
+  for (int u = 0; u < S1_RPT; ++u) {
+    const cplx v = vcol[u];
+#pragma unroll
+    for (int c = IC + 1; c < SB; ++c) {
+      const cplx x = PGET(u, c);
+      ws[2 * (c - 1)] += v.x * x.x + v.y * x.y;
+      ws[2 * (c - 1) + 1] += v.x * x.y - v.y * x.x;
+    }
+#pragma unroll
+    for (int pc = 0; pc < IC; ++pc) {
+      const cplx x = PGET(u, pc);  // rows >= IC > pc lie below the unit of column pc; v is 0 on the others
+      ws[2 * pc] += x.x * v.x + x.y * v.y;
+      ws[2 * pc + 1] += x.x * v.y - x.y * v.x;
+    }
+  }
+  cta_sum<2 * (SB - 1)>(ws, red);
+  const cplx ct = cconj(tau);
+#pragma unroll
+  for (int u = 0; u < S1_RPT; ++u) {
+    const cplx tv = cmul(ct, vcol[u]);
+#pragma unroll
+    for (int c = IC + 1; c < SB; ++c) {
+      cplx x = PGET(u, c);
+      cfms(x, tv, mk(ws[2 * (c - 1)], ws[2 * (c - 1) + 1]));
+      PSET(u, c, x);
+    }
+  }
+  if (t < IC) {
+    cplx acc = mk(0, 0);
+#pragma unroll
+    for (int l = 0; l < IC; ++l)
+      if (l >= t) cfma(acc, sTq[t + SB * l], mk(ws[2 * l], ws[2 * l + 1]));
+    sTq[t + SB * IC] = cmul(mk(-tau.x, -tau.y), acc);
+  } else if (t == IC) {
+    sTq[t + SB * IC] = tau;
+  }
+}
+
+__device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* red, cplx* sbc, cplx* sTq, cplx* sP) {
   const int n = a.n, t = threadIdx.x;
   const int m = n - j - SB;
   const int bw = min(SB, m - 1);
-  cplx P[8][SB];
+  cplx PR[S1_RPT][4];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int ir = t + 256 * u;
+  for (int u = 0; u < S1_RPT; ++u) {
+    const int ir = t + S1_NT * u;
 #pragma unroll
-    for (int c = 0; c < SB; ++c) P[u][c] = (ir < m) ? ldcg_c(a.A + (long)(j + c) * a.lda + (j + SB + ir)) : mk(0, 0);
+    for (int c = 0; c < SB; ++c) {
+      const cplx x = (ir < m) ? ldcg_c(a.A + (long)(j + c) * a.lda + (j + SB + ir)) : mk(0, 0);
+      PSET(u, c, x);
+    }
   }
   if (t < 64) {  // diagonal block -> band
     const int rr = t & 7, cc = t >> 3;
@@ -141,118 +253,66 @@ __device__ __noinline__ void panel_qr(const S1Args& a, int j, int p, double* red
   double betav[SB];
   // sTq: T factor, row pr written by thread pr only (T(pr, q) = -tau_q sum_l T(pr, l) G(l, q), G = V^H V)
   if (t < 64) sTq[t] = mk(0, 0);
-#pragma unroll
-  for (int ic = 0; ic < SB; ++ic) {
-    tauv[ic] = mk(0, 0);
-    betav[ic] = 0.0;
-    if (ic < bw) {
-      double part[1] = {0.0};
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int ir = t + 256 * u;
-        if (ir > ic) part[0] += cabs2(P[u][ic]);
-      }
-      if (t == ic) sbc[0] = P[0][ic];
-      cta_sum<1>(part, red);
-      const cplx alpha = sbc[0];
-      double beta;
-      cplx tau, scal;
-      larfg(alpha, part[0], beta, tau, scal);
-      tauv[ic] = tau;
-      betav[ic] = beta;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int ir = t + 256 * u;
-        if (ir > ic)
-          P[u][ic] = cmul(P[u][ic], scal);
-        else if (ir == ic)
-          P[u][ic] = mk(1, 0);
-      }
-      // one reduction of 7 complex numbers: slots c-1 (c > ic): w_c = v^H P(:, c) for the panel update;
-      // slots pc (pc < ic): G(pc, ic) = v_pc^H v_ic for the T factor
-      double ws[2 * (SB - 1)];
-#pragma unroll
-      for (int x = 0; x < 2 * (SB - 1); ++x) ws[x] = 0.0;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int ir = t + 256 * u;
-        if (ir >= ic) {
-          const cplx v = P[u][ic];
-#pragma unroll
-          for (int c = ic + 1; c < SB; ++c) {
-            const cplx x = P[u][c];
-            ws[2 * (c - 1)] += v.x * x.x + v.y * x.y;
-            ws[2 * (c - 1) + 1] += v.x * x.y - v.y * x.x;
-          }
-#pragma unroll
-          for (int pc = 0; pc < ic; ++pc) {
-            const cplx x = P[u][pc];  // ir >= ic > pc: below the unit of column pc
-            ws[2 * pc] += x.x * v.x + x.y * v.y;
-            ws[2 * pc + 1] += x.x * v.y - x.y * v.x;
-          }
-        }
-      }
-      cta_sum<2 * (SB - 1)>(ws, red);
-      const cplx ct = cconj(tau);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int ir = t + 256 * u;
-        if (ir >= ic) {
-#pragma unroll
-          for (int c = ic + 1; c < SB; ++c) cfms(P[u][c], cmul(ct, P[u][ic]), mk(ws[2 * (c - 1)], ws[2 * (c - 1) + 1]));
-        }
-      }
-      if (t < ic) {
-        cplx acc = mk(0, 0);
-#pragma unroll
-        for (int l = 0; l < ic; ++l)
-          if (l >= t) cfma(acc, sTq[t + SB * l], mk(ws[2 * l], ws[2 * l + 1]));
-        sTq[t + SB * ic] = cmul(mk(-tau.x, -tau.y), acc);
-      } else if (t == ic) {
-        sTq[t + SB * ic] = tau;
-      }
-    }
-  }
+  qr_column<0>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<1>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<2>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<3>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<4>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<5>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<6>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
+  qr_column<7>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
   __syncthreads();
   if (t < 64) reinterpret_cast<cplx*>(a.small + 256 * p + 128)[t] = sTq[t];
-  if (t < SB) a.taus[j + t] = mk(0, 0);
-  __syncthreads();
+  if (t < SB) {
+    cplx tv = mk(0, 0);
 #pragma unroll
-  for (int c = 0; c < SB; ++c)
-    if (t == 0) a.taus[j + c] = tauv[c];
+    for (int c = 0; c < SB; ++c)
+      if (t == c) tv = tauv[c];
+    a.taus[j + t] = tv;
+  }
   // band entries of the R factor (rows j+8+ir, ir <= c) and explicit reflectors
   cplx* Vp = a.Vb + (long)p * a.bstride;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int ir = t + 256 * u;
+  for (int u = 0; u < S1_RPT; ++u) {
+    const int ir = t + S1_NT * u;
     if (ir < m) {
+      cplx vrow[SB];
 #pragma unroll
       for (int c = 0; c < SB; ++c) {
+        const cplx pv = PGET(u, c);
         if (ir <= c) {
-          cplx x = P[u][c];
+          cplx x = pv;
           if (ir == c && c < bw) x = mk(betav[c], 0);
           a.Bd[(long)LDB * (j + c) + (SB + ir - c)] = x;
         }
         cplx v = mk(0, 0);
-        if (c < bw) v = (ir < c) ? mk(0, 0) : ((ir == c) ? mk(1, 0) : P[u][c]);
-        Vp[(long)(j + SB + ir) * SB + c] = v;
+        if (c < bw) v = (ir < c) ? mk(0, 0) : ((ir == c) ? mk(1, 0) : pv);
+        vrow[c] = v;
         a.A[(long)(j + c) * a.lda + (j + SB + ir)] = v;
       }
+#pragma unroll
+      for (int c = 0; c < SB; ++c) Vp[(long)(j + SB + ir) * SB + c] = vrow[c];
     }
   }
 }
+#undef PGET
+#undef PSET
 
-__global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
-  __shared__ double red[14 * 8];
+__global__ void __launch_bounds__(S1_NT, 1) sbr_stage1_kernel(S1Args a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];  // panel QR: columns 4..7 of the panel (4 x QR_MP complex)
+  __shared__ double red[14 * S1_NW];
   __shared__ cplx sbc[4];
   __shared__ cplx sT[64], sS[64], sX[64], sM[64];
   __shared__ cplx sWc[9 * 8], sVc[9 * 8];
   __shared__ cplx sOp[3][OPS];
-  __shared__ cplx sSp[8][64];
+  cplx(*sSp)[64] = reinterpret_cast<cplx(*)[64]>(dyn_smem);  // pass only (the panel QR is done by then)
   const int n = a.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x;
   const int NB = (n >= SB + 2) ? (n - 2 - SB) / SB + 1 : 0;  // blocks j = 8 bi with j + 8 <= n - 2
   unsigned epoch = 0;
+#ifdef TEVO_SBR_TIMING
+  long long _t0 = clock64();
+#endif
   for (int bi = 0; bi <= NB; ++bi) {
     const int j = SB * bi;
     const int p = bi & 1, pp = p ^ 1;
@@ -299,7 +359,7 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
       }
       __syncthreads();
       const int q = lane & 7, sub = lane >> 3;
-      for (long rb = j + (long)blockIdx.x * 32 + warp * 4; rb < n; rb += 32L * G) {
+      for (long rb = j + (long)blockIdx.x * (4 * S1_NW) + warp * 4; rb < n; rb += (long)(4 * S1_NW) * G) {
         // the loop bound is warp-uniform (the shuffles below need all lanes); rows past the end are inactive
         const long r = rb + sub;
         const bool act = r < n;
@@ -338,13 +398,15 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
     // accumulators of block bi
     {
       double* Yz = a.Yb + 2 * (long)p * a.bstride;
-      for (long e = (long)blockIdx.x * 256 + tid; e < 2L * (n + 8) * SB; e += 256L * G) Yz[e] = 0.0;
+      for (long e = (long)blockIdx.x * S1_NT + tid; e < 2L * (n + 8) * SB; e += (long)S1_NT * G) Yz[e] = 0.0;
       if (blockIdx.x == 0 && tid < 128) a.small[256 * p + tid] = 0.0;
     }
+    ST_MARK(0);
     grid_bar(a.bar, ++epoch);
+    ST_MARK(1);
     if (bi == NB) {
       // remaining columns j .. n-1: all inside the band
-      for (int e = blockIdx.x * 256 + tid; e < ncol * ncol; e += 256 * G) {
+      for (int e = blockIdx.x * S1_NT + tid; e < ncol * ncol; e += S1_NT * G) {
         const int rr = e % ncol, cc = e / ncol;
         if (rr >= cc) {
           cplx x = ldcg_c(a.A + (long)(j + cc) * a.lda + (j + rr));
@@ -356,15 +418,21 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
       break;
     }
     // ---------------- (2) panel QR of block bi ----------------
-    if (blockIdx.x == 0) panel_qr(a, j, p, red, sbc, sX);
+    if (blockIdx.x == 0) panel_qr(a, j, p, red, sbc, sX, reinterpret_cast<cplx*>(dyn_smem));
+    ST_MARK(2);
     grid_bar(a.bar, ++epoch);
+    ST_MARK(3);
     // ---------------- (3) one pass over A[R, R], R = j+8 .. n-1: update of block bi-1, Y = A V, S = V^H Y ----------------
     {
       const int r_lo = j + SB, m = n - r_lo;
+      constexpr int TR = 8 * S1_NW;  // tile: TR rows (8 per warp) x 64 columns
       const int nt = (m + 63) / 64;
-      const int ntiles = nt * nt;
-      const int chunk = (ntiles + G - 1) / G;
-      const int t_lo = blockIdx.x * chunk, t_hi = min(ntiles, t_lo + chunk);
+      const int ntr = (m + TR - 1) / TR;
+      const int ntiles = ntr * nt;
+      // contiguous, balanced ranges of the row-major tile list (a CTA mostly stays inside one row block)
+      const int tbase = ntiles / G, trem = ntiles % G;
+      const int t_lo = blockIdx.x * tbase + min((int)blockIdx.x, trem);
+      const int t_hi = t_lo + tbase + ((int)blockIdx.x < trem ? 1 : 0);
       const bool has_prev = bi > 0;
       const cplx* Vprev = a.Vb + (long)pp * a.bstride;
       const cplx* Wprev = a.Wb + (long)pp * a.bstride;
@@ -410,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
         if (tid < 64) {
           cplx acc = mk(0, 0);
 #pragma unroll
-          for (int w = 0; w < 8; ++w) acc = cadd(acc, sSp[w][tid]);
+          for (int w = 0; w < S1_NW; ++w) acc = cadd(acc, sSp[w][tid]);
           atomicAdd(Sacc + 2 * tid, acc.x);
           atomicAdd(Sacc + 2 * tid + 1, acc.y);
         }
@@ -421,7 +489,7 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
         if (I != curI) {
           if (curI >= 0) flush();
           curI = I;
-          r = r_lo + 64L * I + rl;
+          r = r_lo + (long)TR * I + rl;
 #pragma unroll
           for (int q = 0; q < SB; ++q) {
             yacc[q] = mk(0, 0);
@@ -431,7 +499,7 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
         }
         const long c0 = r_lo + 64L * J;
         __syncthreads();  // the previous tile's operand rows are no longer read
-        for (int e = tid; e < 64 * SB; e += 256) {
+        for (int e = tid; e < 64 * SB; e += S1_NT) {
           const int c = e >> 3, q = e & 7;
           const long cg_ = c0 + c;
           const bool in = cg_ < n;
@@ -440,29 +508,36 @@ __global__ void __launch_bounds__(256, 1) sbr_stage1_kernel(S1Args a) {
           sOp[2][opi(c, q)] = in ? ldcg_c(Vnew + cg_ * SB + q) : mk(0, 0);
         }
         __syncthreads();
-        cplx av[16];
         cplx* ap = a.A + (c0 + 16 * cgp) * a.lda + r;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) av[i] = (r < n && c0 + 16 * cgp + i < n) ? ldcg_c(ap + (long)i * a.lda) : mk(0, 0);
+        for (int h = 0; h < 2; ++h) {  // the 16 columns of the thread in two batches of 8 loads in flight
+          cplx av[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int c = 16 * cgp + i;
-          cplx x = av[i];
-          if (has_prev) {
+          for (int i = 0; i < 8; ++i)
+            av[i] = (r < n && c0 + 16 * cgp + 8 * h + i < n) ? ldcg_c(ap + (long)(8 * h + i) * a.lda) : mk(0, 0);
 #pragma unroll
-            for (int q = 0; q < SB; ++q) {
-              cfms(x, vp[q], cconj(sOp[0][opi(c, q)]));
-              cfms(x, wp[q], cconj(sOp[1][opi(c, q)]));
+          for (int i = 0; i < 8; ++i) {
+            const int c = 16 * cgp + 8 * h + i;
+            cplx x = av[i];
+            if (has_prev) {
+#pragma unroll
+              for (int q = 0; q < SB; ++q) {
+                cfms(x, vp[q], cconj(sOp[0][opi(c, q)]));
+                cfms(x, wp[q], cconj(sOp[1][opi(c, q)]));
+              }
+              if (r < n && c0 + c < n) ap[(long)(8 * h + i) * a.lda] = x;
             }
-            if (r < n && c0 + c < n) ap[(long)i * a.lda] = x;
-          }
 #pragma unroll
-          for (int q = 0; q < SB; ++q) cfma(yacc[q], x, sOp[2][opi(c, q)]);
+            for (int q = 0; q < SB; ++q) cfma(yacc[q], x, sOp[2][opi(c, q)]);
+          }
         }
       }
+      ST_MARK(4);
       if (curI >= 0) flush();
+      ST_MARK(5);
     }
     grid_bar(a.bar, ++epoch);
+    ST_MARK(6);
   }
 }
 
@@ -638,8 +713,7 @@ __global__ void __launch_bounds__(256) band_chase_kernel(int n, cplx* __restrict
 #pragma unroll
       for (int i = 0; i < 4; ++i) vr[i] = vr2[i];
       __syncwarp();
-      if (lane == 0) {
-        __threadfence();
+      if (lane == 0) {  // the release store orders the window stores of all lanes (made visible to lane 0 by __syncwarp)
         const int val = (k + 1 == Ks) ? DONE : k + 1;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(prog + s), "r"(val) : "memory");
       }
@@ -657,50 +731,90 @@ __global__ void __launch_bounds__(256) band_chase_kernel(int n, cplx* __restrict
 // tridiagonal matrix.  Shared layout: row r of local column q at  q*npad + (r & 7)*(npad/8) + (r >> 3)  so that the
 // threads of a warp (consecutive reflectors = row offsets 8 apart) touch consecutive addresses.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) q2_apply_kernel(int n, int k, int NC, const double* __restrict__ Z, long ldz,
+constexpr int Q2_NT = 512;
+__global__ void __launch_bounds__(Q2_NT) q2_apply_kernel(int n, int k, int NC, const double* __restrict__ Z, long ldz,
                                                        const int* __restrict__ perm, const cplx* __restrict__ RV, int KS,
                                                        cplx* __restrict__ U, long ldu) {
   extern __shared__ __align__(16) unsigned char smraw[];
   cplx* X = reinterpret_cast<cplx*>(smraw);
   const int npad = (n + 7) & ~7;
   const int n8 = npad >> 3;
+  cplx* Rb = X + (size_t)NC * npad;  // two buffers of KS*9 entries: the reflectors of the current and the next sweep
+  const int rvsz = KS * 9;
   const int col0 = blockIdx.x * NC;
   const int nc = min(NC, k - col0);
   if (nc <= 0) return;
   const int tid = threadIdx.x;
+  auto stage = [&](int s, int buf) {
+    const int cnt = ((n - 1 - s + SB - 1) / SB) * 9;
+    const cplx* src = RV + (long)s * rvsz;
+    cplx* dst = Rb + (size_t)buf * rvsz;
+    for (int e = tid; e < cnt; e += Q2_NT) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(n - 2, 0);
   for (int q = 0; q < nc; ++q) {
     const double* zc = Z + (long)(perm ? perm[col0 + q] : col0 + q) * ldz;
     for (int r = tid; r < npad; r += blockDim.x)
       X[q * npad + (r & 7) * n8 + (r >> 3)] = (r < n) ? mk(zc[r], 0.0) : mk(0, 0);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int s = n - 2; s >= 0; --s) {
+    const int buf = (n - 2 - s) & 1;
+    if (s > 0) stage(s - 1, buf ^ 1);  // that buffer was last read two sweeps ago (a barrier lies in between)
+    const cplx* R = Rb + (size_t)buf * rvsz;
     const int Ks = (n - 1 - s + SB - 1) / SB;
     const int ntask = Ks * nc;
-    for (int id = tid; id < ntask; id += blockDim.x) {
-      const int kk = id % Ks, q = id / Ks;
-      const cplx* rv = RV + ((long)s * KS + kk) * 9;
-      const cplx tau = rv[SB];
-      if (tau.x == 0.0 && tau.y == 0.0) continue;
-      const int r0 = s + 1 + SB * kk;
-      cplx* xq = X + q * npad;
-      cplx x[SB], v[SB];
-      cplx dot = mk(0, 0);
+    // two independent (reflector, column) tasks per iteration: the dot-product / update chains of one task are
+    // latency bound, a second one in flight hides them
+    for (int id = tid; id < ntask; id += 2 * Q2_NT) {
+      const int idb = id + Q2_NT;
+      const bool hb = idb < ntask;
+      const int ka = id % Ks, qa = id / Ks;
+      const int kb = hb ? idb % Ks : ka, qb = hb ? idb / Ks : qa;
+      const cplx* rva = R + ka * 9;
+      const cplx* rvb = R + kb * 9;
+      const cplx taua = rva[SB];
+      const cplx taub = hb ? rvb[SB] : mk(0, 0);
+      const int ra = s + 1 + SB * ka, rb = s + 1 + SB * kb;
+      cplx* xqa = X + qa * npad;
+      cplx* xqb = X + qb * npad;
+      cplx xa[SB], va[SB], xb[SB], vb[SB];
+      cplx da0 = mk(0, 0), da1 = mk(0, 0), db0 = mk(0, 0), db1 = mk(0, 0);
 #pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        const int r = r0 + i;  // r < npad always holds for rows with v != 0; padded rows hold zeros
-        v[i] = rv[i];
-        x[i] = (r < npad) ? xq[(r & 7) * n8 + (r >> 3)] : mk(0, 0);
-        cfma_conj(dot, v[i], x[i]);
+      for (int i = 0; i < SB; ++i) {  // rows past the end carry v = 0 and are neither read nor written
+        va[i] = rva[i];
+        vb[i] = rvb[i];
+        xa[i] = (ra + i < npad) ? xqa[((ra + i) & 7) * n8 + ((ra + i) >> 3)] : mk(0, 0);
+        xb[i] = (hb && rb + i < npad) ? xqb[((rb + i) & 7) * n8 + ((rb + i) >> 3)] : mk(0, 0);
       }
-      const cplx td = cmul(tau, dot);
+#pragma unroll
+      for (int i = 0; i < SB; i += 2) {
+        cfma_conj(da0, va[i], xa[i]);
+        cfma_conj(da1, va[i + 1], xa[i + 1]);
+        cfma_conj(db0, vb[i], xb[i]);
+        cfma_conj(db1, vb[i + 1], xb[i + 1]);
+      }
+      const cplx tda = cmul(taua, cadd(da0, da1));
+      const cplx tdb = cmul(taub, cadd(db0, db1));
 #pragma unroll
       for (int i = 0; i < SB; ++i) {
-        const int r = r0 + i;
-        cfms(x[i], v[i], td);
-        if (r < npad) xq[(r & 7) * n8 + (r >> 3)] = x[i];
+        cfms(xa[i], va[i], tda);
+        if (ra + i < npad) xqa[((ra + i) & 7) * n8 + ((ra + i) >> 3)] = xa[i];
+      }
+      if (hb) {
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+          cfms(xb[i], vb[i], tdb);
+          if (rb + i < npad) xqb[((rb + i) & 7) * n8 + ((rb + i) >> 3)] = xb[i];
+        }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
   for (int q = 0; q < nc; ++q)
@@ -708,6 +822,18 @@ __global__ void __launch_bounds__(256) q2_apply_kernel(int n, int k, int NC, con
 }
 
 }  // namespace
+
+#ifdef TEVO_SBR_TIMING
+extern "C" int tevo_debug_sbr_cycles(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_sbr_cycles, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_sbr_cycles, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 // ==================================================================================================================
 // host side
@@ -759,7 +885,12 @@ void Sbr::reduce_to_band(cudaStream_t st, int n, cplx* A, long lda, cplx* taus, 
   if (max_ctas > 0) grid = std::min(grid, max_ctas);
   grid = std::max(1, grid);
   void* args[] = {&a};
-  TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sbr_stage1_kernel, dim3(grid), dim3(256), args, 0, st));
+  const size_t qr_smem = sizeof(cplx) * 4 * (size_t)QR_MP;
+  static PerDeviceOnce once;
+  once([&]() {
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(sbr_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qr_smem));
+  });
+  TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)sbr_stage1_kernel, dim3(grid), dim3(S1_NT), args, qr_smem, st));
   TEVO_LAUNCHED();
   sbr_zero_upper_kernel<<<n, 128, 0, st>>>(n, A, lda);
   TEVO_LAUNCHED();
@@ -788,11 +919,15 @@ void Sbr::apply_q2(cudaStream_t st, int n, int k, const double* Z, long ldz, con
   });
   const int npad = (n + 7) & ~7;
   const size_t per_col = (size_t)npad * sizeof(cplx);
-  int ncmax = (int)((size_t)(227 * 1024) / per_col);
-  if (ncmax < 1) throw TevoError(1, "sbr: matrix too large for the shared-memory back-transformation");
-  int NC = std::min(ncmax, std::max(1, (k + num_sms_ - 1) / num_sms_));
+  const size_t rv_bytes = (size_t)2 * ks_ * 9 * sizeof(cplx);  // reflectors of two sweeps (double buffer)
+  const size_t budget = (size_t)227 * 1024;
+  if (rv_bytes + per_col > budget) throw TevoError(1, "sbr: matrix too large for the shared-memory back-transformation");
+  const int ncmax = (int)((budget - rv_bytes) / per_col);
+  // as many columns per CTA as fit, but no more than an even split of the k columns over whole waves of CTAs needs
+  const int waves = std::max(1, (k + ncmax * num_sms_ - 1) / (ncmax * num_sms_));
+  int NC = std::min(ncmax, std::max(1, (k + waves * num_sms_ - 1) / (waves * num_sms_)));
   const int grid = (k + NC - 1) / NC;
-  q2_apply_kernel<<<grid, 256, (size_t)NC * per_col, st>>>(n, k, NC, Z, ldz, perm_dev, RV_, ks_, U, ldu);
+  q2_apply_kernel<<<grid, Q2_NT, (size_t)NC * per_col + rv_bytes, st>>>(n, k, NC, Z, ldz, perm_dev, RV_, ks_, U, ldu);
   TEVO_LAUNCHED();
 }
 

@@ -346,4 +346,147 @@ function onesite!(PH::DeviceProjMPO, dpsi::DeviceMPS, i::Int, t::Number; hermiti
     check(dpsi.ctx, st)
 end
 
+# ---- drop-in drivers: tebd!(psi::MPS, ...) / tdvp!(psi::MPS, H::MPO, ...) behind the reference signatures ------------
+# The schedule (time_evo_gates, bunching, direction alternation, callback arguments) is TimeEvoMPS.jl's own code path
+# restated line by line from src/tebd.jl:91-179 and src/tdvp.jl:37-96; only the arithmetic call sites are replaced:
+#   apply_gates!(psi, U; ...)            -> TevoB200.apply_gates!(dpsi, U; ...)          (src/bondgate.jl:55-63)
+#   position! / exponentiate / replacebond! -> TevoB200.twosite! / onesite!              (src/tdvp.jl:58-64,77-83)
+# The state lives on the device for the whole call: upload once, download once at the end.  Callbacks keep the
+# reference protocol apply!(cb, psi; t, bond, spec, sweepdir, sweepend, alg); what they may read from `psi` decides
+# how much is copied back before each invocation (state_needed below).
+import TimeEvoMPS
+import TimeEvoMPS: TEBDalg, TEBD2, TEBD4, TDVP2, BondGate, GateList, BondOperator, gates, time_evo_gates, bond,
+                   TEvoCallback, NoTEvoCallback, LocalMeasurementCallback, SpecCallback, apply!, checkdone!, callback_dt
+
+"What a callback reads from `psi`: :nothing (spec only), :bond (psi[bond], psi[bond+1] at sweep-end gates, as
+LocalMeasurementCallback does at src/callback.jl:89) or :all (unknown user callback: the whole state, every gate)."
+state_needed(::NoTEvoCallback) = :nothing
+state_needed(::SpecCallback) = :nothing
+state_needed(::LocalMeasurementCallback) = :bond
+state_needed(::TEvoCallback) = :all
+
+"Copy sites `js` of the device state back into `psi` (link indices are renewed consistently for all of them)."
+function download_sites!(psi::MPS, dpsi::DeviceMPS, js)
+    N = length(psi)
+    dims = Vector{Cint}(undef, N - 1)
+    check(dpsi.ctx, ccall((:tevo_mps_bonddims, LIB), Cint, (Ptr{Cvoid}, Ptr{Cint}), dpsi.h, dims))
+    # links touching the requested sites get fresh indices; a site outside `js` that shares one of them keeps a stale
+    # tensor, which is why :bond callbacks may only contract psi[bond]*psi[bond+1] (exactly what callback.jl:89 does)
+    newlink = Dict{Int,Index}()
+    for j in js, b in (j - 1, j)
+        1 <= b <= N - 1 && !haskey(newlink, b) && (newlink[b] = Index(dims[b], dpsi.linktags[b]))
+    end
+    for j in js
+        chil = j > 1 ? dims[j - 1] : 1
+        chir = j < N ? dims[j] : 1
+        A = Array{ComplexF64}(undef, chil, dim(dpsi.sites[j]), chir)
+        GC.@preserve A check(dpsi.ctx, ccall((:tevo_mps_download_site, LIB), Cint,
+                                             (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Csize_t), dpsi.h, j - 1, A, length(A)))
+        is = filter(!isnothing, (j > 1 ? newlink[j - 1] : nothing, dpsi.sites[j], j < N ? newlink[j] : nothing))
+        psi[j] = ITensor(reshape(A, map(dim, is)...), is...)
+    end
+    return psi
+end
+
+function sync_for_callback!(psi::MPS, dpsi::DeviceMPS, cb, b::Int, sweepend::Bool)
+    need = state_needed(cb)
+    need === :all && return download!(psi, dpsi)
+    need === :bond && sweepend && return download_sites!(psi, dpsi, (b, b + 1))
+    return psi
+end
+
+"tebd!(psi, H, dt, tf, alg; kwargs...) with the arithmetic on the B200 (src/tebd.jl:89-179, same keywords)."
+tebd!(psi::MPS, H::BondOperator, args...; kwargs...) = tebd!(psi, gates(H), args...; kwargs...)
+function tebd!(psi::MPS, H::GateList, dt::Number, tf::Number, alg::TEBDalg=TEBD2(); ctx::Ctx=Ctx(), kwargs...)
+    nsteps = Int(tf / dt)                                                        # :95 (InexactError as upstream)
+    ishermitian = get(kwargs, :ishermitian, false)                               # :100
+    cb = get(kwargs, :callback, NoTEvoCallback())                                # :102
+    orthogonalize_step = get(kwargs, :orthogonalize, 0)                          # :110
+    dtm = callback_dt(cb)
+    if dtm > 0                                                                   # :113-120
+        floor(Int64, dtm / dt) != dtm / dt &&
+            throw("Measurement time step $dtm incommensurate with time-evolution time step $dt")
+        nbunch = gcd(floor(Int64, dtm / dt), nsteps)
+    else
+        nbunch = nsteps
+    end
+    orthogonalize_step > 0 && (nbunch = gcd(nbunch, orthogonalize_step))         # :121
+    Ustart, Us, Uend = time_evo_gates(dt, H, alg; ishermitian=ishermitian)       # :123
+    length(Ustart) == 0 && length(Uend) == 0 && (nbunch += 1)                    # :125
+    trunc_kw = filter(kv -> kv[1] in (:maxdim, :mindim, :cutoff, :use_absolute_cutoff, :normalize), kwargs)
+    dpsi = upload(psi; ctx=ctx)
+    pairs_of(U) = Tuple{ITensor,Int}[(g.G, bond(g)) for g in U]
+    function cb_func(dt, step, rev, se)                                          # :103-109
+        cb isa NoTEvoCallback && return nothing
+        return (d; bond, spec) -> begin
+            sync_for_callback!(psi, d, cb, bond, se)
+            apply!(cb, psi; t=dt * step, bond=bond, spec=spec, sweepdir=rev ? "left" : "right", sweepend=se, alg=alg)
+        end
+    end
+    step = 0
+    rev = false
+    while step < nsteps                                                          # :132
+        for U in Ustart                                                          # :133-136
+            apply_gates!(dpsi, pairs_of(U); reversed=rev, trunc_kw...)
+            rev = !rev
+        end
+        for i in 1:nbunch-1                                                      # :138-153
+            for U in Us
+                apply_gates!(dpsi, pairs_of(U); reversed=rev, cb=cb_func(dt, step, rev, false), trunc_kw...)
+                rev = !rev
+            end
+            step += 1
+            checkdone!(cb, psi) && break
+        end
+        for (i, U) in enumerate(Uend)                                            # :157-160
+            apply_gates!(dpsi, pairs_of(U); reversed=rev, cb=cb_func(dt, step + 1, rev, i >= length(Uend) - 1), trunc_kw...)
+            rev = !rev
+        end
+        length(Uend) > 0 && (step += 1)                                          # :163
+        (orthogonalize_step > 0 && step % orthogonalize_step == 0) && reorthogonalize!(dpsi)   # :174
+        checkdone!(cb, psi) && break                                             # :176
+    end
+    download!(psi, dpsi)
+    return psi
+end
+
+"tdvp!(psi, H::MPO, dt, tf; kwargs...) with the arithmetic on the B200 (src/tdvp.jl:37-96, same keywords)."
+function tdvp!(psi::MPS, H::MPO, dt::Number, tf::Number; ctx::Ctx=Ctx(), kwargs...)
+    nsteps = Int(tf / dt)                                                        # :38
+    cb = get(kwargs, :callback, NoTEvoCallback())
+    hermitian = get(kwargs, :hermitian, true)
+    exp_tol = get(kwargs, :exp_tol, 1e-14)
+    krylovdim = get(kwargs, :krylovdim, 30)
+    maxiter = get(kwargs, :maxiter, 100)
+    normalize = get(kwargs, :normalize, true)                                    # :39-44
+    τ = 1im * dt
+    imag(τ) == 0 && (τ = real(τ))                                                # :47-48
+    N = length(psi)
+    trunc_kw = filter(kv -> kv[1] in (:maxdim, :mindim, :cutoff, :use_absolute_cutoff, :absoluteCutoff), kwargs)
+    dpsi = upload(psi; ctx=ctx)
+    orthogonalize!(dpsi, 1)                                                      # :51
+    PH = DeviceProjMPO(H, dpsi)                                                  # :52
+    position!(PH, dpsi, 1)                                                       # :53
+    for s in 1:nsteps                                                            # :54
+        for (b, ha) in sweepnext(N)                                              # :56
+            spec = twosite!(PH, dpsi, b, -τ / 2; hermitian=hermitian, exp_tol=exp_tol, krylovdim=krylovdim,
+                            ortho=ha == 1 ? "left" : "right", normalize=normalize, trunc_kw...)      # :58-64
+            if !(cb isa NoTEvoCallback)
+                sync_for_callback!(psi, dpsi, cb, b, ha == 2)
+                apply!(cb, psi; t=s * dt, bond=b, sweepend=ha == 2, sweepdir=ha == 1 ? "right" : "left", spec=spec,
+                       alg=TDVP2())                                              # :67-72
+            end
+            i = ha == 1 ? b + 1 : b                                              # :77
+            if 1 < i < N && !(dt isa Complex)
+                onesite!(PH, dpsi, i, τ / 2; hermitian=hermitian, exp_tol=exp_tol, krylovdim=krylovdim, maxiter=maxiter)  # :78-83
+            elseif i == 1 && dt isa Complex
+                normalize_site!(dpsi, i)                                         # :84-87
+            end
+        end
+        checkdone!(cb) && break                                                  # :94
+    end
+    download!(psi, dpsi)
+    return nothing
+end
+
 end # module
