@@ -379,6 +379,7 @@ def run_sharded(args):
     c0 = debug_counters(ctx)
     n0 = ctx.launch_count()
     b0 = sh.bytes_sent
+    x0 = sh.exchange_s
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()
@@ -399,6 +400,8 @@ def run_sharded(args):
     ms_per_step = ms / timed
     value = 1e3 / ms_per_step
     bytes_per_step = int((sh.bytes_sent - b0) / max(timed, 1))
+    # wall time this rank spent inside the boundary exchange (includes waiting for the neighbour = load imbalance)
+    exch_ms = replicas.max_over_ranks((sh.exchange_s - x0) * 1e3 / max(timed, 1), dist, device="cuda")
     # end to end: segment uploaded from pinned host memory, one step, segment downloaded
     e2e = None
     if not args.no_e2e:
@@ -448,6 +451,8 @@ def run_sharded(args):
         "fp64_tensor": {"algorithmic_tflops": flops_step / (ms_per_step * 1e-3) / 1e12, "peak_tflops": zpeak * world,
                         "frac": flops_step / (ms_per_step * 1e-3) / 1e12 / (zpeak * world)},
         "boundary_bytes_sent_per_step_rank0": bytes_per_step,
+        "boundary_exchange_ms_per_step_max_rank": exch_ms,
+        "boundary_transfer_ms_per_step_at_770GBs": bytes_per_step / 770e9 * 1e3,
         "wall_ms_per_step": wall * 1e3 / timed,
         "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
         "budget_s": args.budget, "wall_s": round(budget.elapsed(), 1),
@@ -699,6 +704,8 @@ def run_sequential(args):
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
     if args.impl == "reference":
         run_reference(args)
         return

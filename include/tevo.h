@@ -189,6 +189,10 @@ int tevo_mps_normalize_site(tevo_mps* psi, int i);
 /* C = alpha*op(A)*op(B) + beta*C on host buffers through the DMMA ZGEMM kernel (op: 0=N, 1=T, 2=C) */
 int tevo_test_zgemm(tevo_ctx* ctx, int ta, int tb, int M, int N, int K, tevo_complex alpha, const tevo_complex* A,
                     int lda, const tevo_complex* B, int ldb, tevo_complex beta, tevo_complex* C, int ldc);
+/* device-resident timing of the DMMA ZGEMM: average milliseconds per launch over `reps` launches of
+ * C(MxN) = op(A) op(B) (+ C if accumulate); kind 0 = general, 1 = Hermitian result (N ignored, lower tiles + mirror) */
+int tevo_test_zgemm_time(tevo_ctx* ctx, int kind, int ta, int tb, int M, int N, int K, int accumulate, int reps,
+                         double* ms_out);
 /* truncated split of a host m x n matrix: returns L (m x k) and R (k x n) with L*R ~ theta */
 int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* theta, const tevo_trunc* trunc, int ortho_left,
                     int normalize, tevo_spec* spec, double* eigs, int eigs_cap, tevo_complex* L, tevo_complex* R,

@@ -734,10 +734,13 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   const size_t zero_bytes = sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
   TEVO_CUDA_CHECK(cudaMemsetAsync(Sall_, 0, sizeof(double) * 2 * PW * PW * (size_t)((n + PW - 1) / PW), st));
-  // experimental: hand the last columns to the cluster-resident kernel (tail.cu) once the trailing matrix fits it
+  // the last columns go to the cluster-resident kernel (tail.cu) once the trailing matrix fits the shared memory of
+  // one 16-CTA cluster: validated on the B200 with the eigensolver / split tests at cluster sizes 1, 8 and 16 and
+  // measured at -5 % (n = 2048) / -14 % (n = 1024) of the panel time (profiles/r02_deferred_checks.log).
+  // TEVO_CLUSTER_TAIL=0 switches it off, another value selects the cluster size.
   static const int tail_cluster = [] {
     const char* e = getenv("TEVO_CLUSTER_TAIL");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 16;
   }();
   static const int tail_max = tail_cluster > 0 ? tridiag_tail_max_m(tail_cluster) : 0;
   int tail_t0 = -1;

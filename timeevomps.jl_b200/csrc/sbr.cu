@@ -50,12 +50,18 @@ __device__ inline void larfg(cplx alpha, double xn2, double& beta, cplx& tau, cp
     scal = mk(0, 0);
     return;
   }
-  const double nx = sqrt(s2);
+  // |(alpha; x)| and its reciprocal from one reciprocal square root (+ a Newton correction each), 1/|alpha - beta|^2
+  // from one reciprocal: dependent FP64 operations cost ~45 cycles each on this part and this chain sits on the
+  // critical path of every reflector (same sequence as the one-stage panel kernel, heig.cu)
+  double rs = rsqrt(s2);
+  double nx = s2 * rs;
+  nx = fma(0.5 * rs, fma(-nx, nx, s2), nx);
+  rs = fma(rs, fma(-nx, rs, 1.0), rs);
   beta = -copysign(nx, alpha.x);
-  const double ib = 1.0 / beta;
+  const double ib = -copysign(rs, alpha.x);
   tau = mk((beta - alpha.x) * ib, -alpha.y * ib);
   const cplx den = mk(alpha.x - beta, alpha.y);
-  const double rdn = 1.0 / cabs2(den);
+  const double rdn = __drcp_rn(cabs2(den));
   scal = mk(den.x * rdn, -den.y * rdn);
 }
 
@@ -121,10 +127,15 @@ __device__ inline void cta_sum(double (&v)[NV], double* red) {
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    double x = 0.0;
+    // pairwise tree (4 dependent additions instead of 16): dependent FP64 operations are what this kernel waits for
+    double x[S1_NW];
 #pragma unroll
-    for (int w = 0; w < S1_NW; ++w) x += red[i * S1_NW + w];
-    v[i] = x;
+    for (int w = 0; w < S1_NW; ++w) x[w] = red[i * S1_NW + w];
+#pragma unroll
+    for (int st = S1_NW / 2; st > 0; st >>= 1)
+#pragma unroll
+      for (int w = 0; w < st; ++w) x[w] += x[w + st];
+    v[i] = x[0];
   }
 }
 

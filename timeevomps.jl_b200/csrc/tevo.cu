@@ -1385,6 +1385,46 @@ extern "C" int tevo_test_zgemm(tevo_ctx* ctx, int ta, int tb, int M, int N, int 
   TEVO_CATCH
 }
 
+/* device-resident timing of the DMMA ZGEMM (no host copies in the timed region): reps launches of
+ * C = op(A) op(B) (+ C if accumulate) between two CUDA events on the library stream; kind 0 = zgemm, 1 = zgemm_herm
+ * (M x M result, lower tiles + mirror).  ms_out = average milliseconds per launch. */
+extern "C" int tevo_test_zgemm_time(tevo_ctx* ctx, int kind, int ta, int tb, int M, int N, int K, int accumulate, int reps,
+                                    double* ms_out) {
+  TEVO_TRY(ctx)
+  require(ctx && ms_out && reps > 0 && M > 0 && N > 0 && K > 0, "tevo_test_zgemm_time: bad argument");
+  const long lda = (ta == 0) ? M : K, ldb = (tb == 0) ? K : N;
+  const size_t na = (size_t)lda * (ta == 0 ? K : M), nb = (size_t)ldb * (tb == 0 ? N : K), nc = (size_t)M * N;
+  DevBuf dA = ctx->alloc(na), dB = ctx->alloc(nb), dC = ctx->alloc(nc);
+  // finite, non-trivial contents: every byte 0x3f gives doubles near 4.7e-4
+  TEVO_CUDA_CHECK(cudaMemsetAsync(dA.p, 0x3f, na * sizeof(cplx), ctx->stream));
+  TEVO_CUDA_CHECK(cudaMemsetAsync(dB.p, 0x3f, nb * sizeof(cplx), ctx->stream));
+  TEVO_CUDA_CHECK(cudaMemsetAsync(dC.p, 0, nc * sizeof(cplx), ctx->stream));
+  const cplx beta = accumulate ? mk(1, 0) : mk(0, 0);
+  auto run = [&]() {
+    if (kind == 1)
+      zgemm_herm(ctx->stream, (Op)ta, (Op)tb, M, K, ONE, dA.p, lda, dB.p, ldb, beta, dC.p, M, true);
+    else
+      zgemm(ctx->stream, (Op)ta, (Op)tb, M, N, K, ONE, dA.p, lda, dB.p, ldb, beta, dC.p, M);
+  };
+  for (int i = 0; i < 3; ++i) run();
+  cudaEvent_t e0, e1;
+  TEVO_CUDA_CHECK(cudaEventCreate(&e0));
+  TEVO_CUDA_CHECK(cudaEventCreate(&e1));
+  TEVO_CUDA_CHECK(cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < reps; ++i) run();
+  TEVO_CUDA_CHECK(cudaEventRecord(e1, ctx->stream));
+  TEVO_CUDA_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  TEVO_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = (double)ms / reps;
+  ctx->release(dA);
+  ctx->release(dB);
+  ctx->release(dC);
+  TEVO_CATCH
+}
+
 extern "C" int tevo_test_split(tevo_ctx* ctx, int m, int n, const tevo_complex* theta, const tevo_trunc* trunc,
                                int ortho_left, int normalize, tevo_spec* spec, double* eigs, int eigs_cap,
                                tevo_complex* L, tevo_complex* R, int kcap) {

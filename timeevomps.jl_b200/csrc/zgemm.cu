@@ -40,6 +40,50 @@ __device__ inline void cp_async_commit() { asm volatile("cp.async.commit_group;\
 template <int N>
 __device__ inline void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- operand staging by the TMA engine: cp.async.bulk (SASS UBLKCP) + mbarrier transaction counts ----
+__device__ inline void mbar_init(unsigned long long* bar, unsigned count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count));
+}
+__device__ inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+__device__ inline void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+// Stage a full (interior) ROWS x BK operand tile with bulk copies issued by one warp: one contiguous run per k
+// (m-contiguous operands: ROWS*16 B) or per row (k-contiguous operands: BK*16 B) into the padded shared-memory rows.
+template <int ROWS, bool KMAJOR>
+__device__ inline void bulk_tile(cplx* s, const cplx* __restrict__ g, long ld, int r0, int k0, unsigned long long* bar,
+                                 int lane) {
+  typedef Tile<ROWS, KMAJOR> T;
+  if (KMAJOR) {
+    for (int r = lane; r < ROWS; r += 32) bulk_g2s(&s[T::idx(r, 0)], g + (long)(r0 + r) * ld + k0, BK * 16, bar);
+  } else {
+    for (int k = lane; k < BK; k += 32) bulk_g2s(&s[T::idx(0, k)], g + (long)(k0 + k) * ld + r0, ROWS * 16, bar);
+  }
+}
+
 __device__ inline void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -71,7 +115,9 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
 // 0 / 1 = compile-time (EXPERIMENTAL, TEVO_ZGEMM_CTSIGN=1, not yet run on hardware): the signs of the imaginary
 // parts then fold into the operand-negation modifiers of DMMA instead of costing 12 FP64 multiplies/negations per
 // k-slice on the pipe the DMMAs use (SASS: the DADD/FSEL/DMUL of the inner loop disappear).
-template <bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB>
+// BULK: full interior tiles (and K a multiple of BK) are staged by the TMA engine (cp.async.bulk + mbarrier) instead
+// of one 16-byte cp.async per element; edge tiles keep the zero-filling cp.async path.
+template <bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB, bool BULK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
@@ -109,27 +155,60 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
     }
 
   const int nk = (K + BK - 1) / BK;
+  __shared__ unsigned long long full_bar[STAGES];
+  const bool bulk = BULK && (m0 + BM <= M) && (n0 + BN <= N) && (K % BK == 0);
+  constexpr unsigned STAGE_BYTES = (unsigned)((BM + BN) * BK * sizeof(cplx));
+  if (bulk) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // fills stage st with k-tile nx (warp 0 issues; the stage was last read before the preceding CTA barrier)
+  auto bulk_fill = [&](int st, int nx) {
+    if (warp == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      if (lane == 0) mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+      __syncwarp();
+      bulk_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, &full_bar[st], lane);
+      bulk_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, &full_bar[st], lane);
+    }
+  };
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<BM, A_KMAJOR>(sA + s * TA::elems, A, lda, m0, s * BK, M, K);
-      load_tile<BN, B_KMAJOR>(sB + s * TB::elems, B, ldb, n0, s * BK, N, K);
+      if (bulk) {
+        bulk_fill(s, s);
+      } else {
+        load_tile<BM, A_KMAJOR>(sA + s * TA::elems, A, lda, m0, s * BK, M, K);
+        load_tile<BN, B_KMAJOR>(sB + s * TB::elems, B, ldb, n0, s * BK, N, K);
+      }
     }
-    cp_async_commit();
+    if (!bulk) cp_async_commit();
   }
 
   const double sa = conjA ? -1.0 : 1.0, sb = conjB ? -1.0 : 1.0;
   for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<STAGES - 2>();
+    if (bulk) {
+      mbar_wait(&full_bar[kt % STAGES], (unsigned)((kt / STAGES) & 1));
+    } else {
+      cp_async_wait<STAGES - 2>();
+    }
     __syncthreads();
     {
       const int nx = kt + STAGES - 1;
       if (nx < nk) {
         const int st = nx % STAGES;
-        load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
-        load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
+        if (bulk) {
+          bulk_fill(st, nx);
+        } else {
+          load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
+          load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
+        }
       }
-      cp_async_commit();
+      if (!bulk) cp_async_commit();
     }
     const cplx* a_s = sA + (kt % STAGES) * TA::elems;
     const cplx* b_s = sB + (kt % STAGES) * TB::elems;
@@ -167,7 +246,7 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
         for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
     }
   }
-  cp_async_wait<0>();
+  if (!bulk) cp_async_wait<0>();
 
   const bool has_beta = (beta.x != 0.0 || beta.y != 0.0);
 #pragma unroll
@@ -189,8 +268,8 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   }
 }
 
-template <bool AK, bool BK_, int CA, int CB>
-void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
+template <bool AK, bool BK_, int CA, int CB, bool BULK>
+void launch_cb(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
               long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
               long bsA, long bsB, long bsC, int lower_only) {
   typedef Tile<BM, AK> TA;
@@ -198,14 +277,35 @@ void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, l
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
   static PerDeviceOnce once;
   once([&]() {
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_, CA, CB>,
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_, CA, CB, BULK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
-  zgemm_dmma_kernel<AK, BK_, CA, CB><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta,
+  zgemm_dmma_kernel<AK, BK_, CA, CB, BULK><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta,
                                                                   C, ldc, splits > 1 ? Kc : K, part_stride, splits,
                                                                   bsA, bsB, bsC, lower_only);
   TEVO_LAUNCHED();
+}
+
+// operand staging: 1 = TMA-engine bulk copies for interior tiles (TEVO_ZGEMM_BULK, see zgemm_bulk_default), 0 = cp.async
+int zgemm_bulk_default() {
+  static const int v = [] {
+    const char* e = getenv("TEVO_ZGEMM_BULK");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+template <bool AK, bool BK_, int CA, int CB>
+void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
+              long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
+              long bsA, long bsB, long bsC, int lower_only) {
+  if (zgemm_bulk_default())
+    launch_cb<AK, BK_, CA, CB, true>(st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc,
+                                     part_stride, batch, bsA, bsB, bsC, lower_only);
+  else
+    launch_cb<AK, BK_, CA, CB, false>(st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc,
+                                      part_stride, batch, bsA, bsB, bsC, lower_only);
 }
 
 template <bool AK, bool BK_>

@@ -63,6 +63,7 @@ class ShardedTEBD:
         self.lo, self.hi = segment_bounds(N, world, rank)
         self.nloc = self.hi - self.lo
         self.bytes_sent = 0
+        self.exchange_s = 0.0     # host wall time spent in the boundary exchange (sends, receives, their syncs)
 
     # ---- point-to-point helpers ----
     def _send(self, t, shape, dst):
@@ -96,7 +97,9 @@ class ShardedTEBD:
         left_cut = self.lo - 1           # bond (lo-1 | lo), owned by rank-1
         has_right = self.rank < self.world - 1 and any(g.b == right_cut for g in gates)
         has_left = self.rank > 0 and any(g.b == left_cut for g in gates)
+        import time as _time
         self.seg.sync()
+        _t0 = _time.perf_counter()
         # 1. boundary tensors travel left: my first site goes to the rank that updates the cut bond
         if has_left:
             t, shape = self.seg.site_tensor(0)
@@ -104,9 +107,11 @@ class ShardedTEBD:
         if has_right:
             t, shape = self._recv(self.rank + 1)
             self.seg.set_site_tensor(self.nloc, t, shape)
+        self.exchange_s += _time.perf_counter() - _t0
         # 2. local updates (all independent)
         out = self.seg.apply_layer([(g.b - self.lo, g.G) for g in mine], **kw)
         self.seg.sync()
+        _t0 = _time.perf_counter()
         # 3. updated boundary tensor and cut-bond Schmidt values travel back right
         if has_right:
             t, shape = self.seg.site_tensor(self.nloc)
@@ -118,6 +123,7 @@ class ShardedTEBD:
             self.seg.set_site_tensor(0, t, shape)
             lt, lshape = self._recv(self.rank - 1, dtype_elems_per_entry=1)
             self.seg.set_lam_tensor(0, lt)
+        self.exchange_s += _time.perf_counter() - _t0
         return out
 
     def run(self, H_gates, dt, nsteps: int, time_evo_gates, alg, **kw):

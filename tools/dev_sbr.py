@@ -11,6 +11,7 @@ import two_stage as ts
 
 ctx = default_ctx()
 lib = load()
+lib.tevo_debug_set_heig_mode(2)   # the two-stage reduction is opt-in
 PD = C.POINTER(C.c_double)
 for n in [int(x) for x in sys.argv[1:]]:
     rng = np.random.default_rng(n)

@@ -11,6 +11,7 @@ from timeevomps_jl_b200._lib import load, check, default_ctx
 import tevo_b200 as t
 ctx = default_ctx()
 lib = load()
+lib.tevo_debug_set_heig_mode(2)   # the two-stage reduction is opt-in
 names = ["mini-phase", "barrier a", "panel QR (CTA 0)", "barrier b", "pass: tiles", "pass: flush", "barrier c"]
 out = (C.c_ulonglong * 16)()
 PD = C.POINTER(C.c_double)
