@@ -51,3 +51,27 @@ def test_product_arm_has_no_cpu_fallback():
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
     msg = p.stderr + p.stdout
     assert "CUDA" in msg or "NVIDIA" in msg or "no CPU fallback" in msg
+
+
+def test_budget_plan_cuts_counts_to_the_wall_clock_budget():
+    """--steps/--warmup are upper bounds: the counts are cut so the run ends inside the budget (round 1's bench ran
+    warmup + 2*steps full steps and was killed by the driver)."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    b = bench.Budget(540.0)
+    b.elapsed = lambda: 95.0              # set-up + Ustart + the wall-timed first warm-up step
+    # 52 s per step, driver asks for 20 + 5: three warm-up steps in total, then what still fits
+    warm_more, timed = b.plan(52.0, 1, 5, 20, reserve=205.0)
+    assert warm_more == 2 and timed == 2
+    assert 95.0 + (warm_more + timed) * 52.0 + 205.0 <= 540.0
+    # a fast configuration runs exactly what was asked for
+    warm_more, timed = b.plan(0.5, 1, 5, 20, reserve=20.0)
+    assert warm_more == 4 and timed == 20
+    # nothing fits: still one timed step, no extra warm-up
+    b.elapsed = lambda: 530.0
+    assert b.plan(52.0, 1, 5, 20, reserve=50.0) == (0, 1)
+    # room for two steps only: one more warm-up, one timed
+    b.elapsed = lambda: 100.0
+    warm_more, timed = b.plan(100.0, 1, 5, 20, reserve=200.0)
+    assert (warm_more, timed) == (1, 1)

@@ -31,7 +31,7 @@ def _herm(n, kind, seed):
 
 def _band_to_dense(band, n):
     B = np.zeros((n, n), dtype=complex)
-    for d in range(9):
+    for d in range(min(9, n)):
         idx = np.arange(n - d)
         B[idx + d, idx] = band[d, :n - d]
         B[idx, idx + d] = np.conj(band[d, :n - d])

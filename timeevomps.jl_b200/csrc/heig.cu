@@ -769,7 +769,10 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     p0 = n;       // skip the one-stage loop
   }
   while (p0 < n - 1) {
-    if (tail_max > 0 && n - p0 <= tail_max && n - p0 >= 2) {
+    // single-lane configuration and matrices of at least 128 rows only: the lanes of the layer-parallel mode keep the
+    // panel kernel (several 16-CTA clusters next to capped cooperative grids were not validated), and tiny problems
+    // gain nothing from a cluster
+    if (tail_max > 0 && max_ctas_ == 0 && n >= 128 && n - p0 <= tail_max && n - p0 >= 2) {
       ProfScope ps(st, P_TRI_PANEL);
       tridiag_tail(st, tail_cluster, n, p0, A, lda, d_, e_, taus_);
       tail_t0 = p0;

@@ -242,6 +242,9 @@ __device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* 
   const int n = a.n, t = threadIdx.x;
   const int m = n - j - SB;
   const int bw = min(SB, m - 1);
+#ifdef TEVO_SBR_TIMING
+  long long _t0 = clock64();
+#endif
   cplx PR[S1_RPT][4];
 #pragma unroll
   for (int u = 0; u < S1_RPT; ++u) {
@@ -252,6 +255,8 @@ __device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* 
       PSET(u, c, x);
     }
   }
+  __syncthreads();
+  ST_MARK(8);
   if (t < 64) {  // diagonal block -> band
     const int rr = t & 7, cc = t >> 3;
     if (rr >= cc) {
@@ -273,6 +278,7 @@ __device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* 
   qr_column<6>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
   qr_column<7>(PR, sP, t, bw, tauv, betav, red, sbc, sTq);
   __syncthreads();
+  ST_MARK(9);
   if (t < 64) reinterpret_cast<cplx*>(a.small + 256 * p + 128)[t] = sTq[t];
   if (t < SB) {
     cplx tv = mk(0, 0);
@@ -281,6 +287,7 @@ __device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* 
       if (t == c) tv = tauv[c];
     a.taus[j + t] = tv;
   }
+  ST_MARK(10);
   // band entries of the R factor (rows j+8+ir, ir <= c) and explicit reflectors
   cplx* Vp = a.Vb + (long)p * a.bstride;
 #pragma unroll
@@ -305,6 +312,8 @@ __device__ __forceinline__ void panel_qr(const S1Args& a, int j, int p, double* 
       for (int c = 0; c < SB; ++c) Vp[(long)(j + SB + ir) * SB + c] = vrow[c];
     }
   }
+  __syncthreads();
+  ST_MARK(11);
 }
 #undef PGET
 #undef PSET
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(256) band_chase_kernel(int n, cplx* __restrict
         if (lane == 0) {
           int v;
           do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog + s - 1) : "memory");
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(prog + s - 1) : "memory");
           } while (v < k + 2);
         }
         __syncwarp();
@@ -738,6 +747,276 @@ __global__ void __launch_bounds__(256) band_chase_kernel(int n, cplx* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// stage 2, second version: the same chase with the hand-offs inside a CTA.  A CTA advances a GROUP of CH_W consecutive
+// sweeps in lock-step (one warp per sweep, warp w runs step T - 2w in slot T, one named barrier per slot), with the
+// part of the band the group is working on in a shared-memory ring of CH_RING columns.  A loader warp streams new
+// columns in ahead of the first sweep (up to CH_L slots ahead, so the L2 latency is off the critical path) and writes
+// finished columns back behind the last sweep; groups follow each other through global progress counters
+// (gprog[g] = F: band columns < last_sweep(g) + 1 + 8 F are final w.r.t. group g and visible in global memory).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CH_W = 16;
+constexpr int CH_NT = (CH_W + 1) * 32;
+constexpr int CH_RING = 512;
+constexpr int CH_L = 8;   // slots the loader may run ahead of the compute warps
+constexpr int CH_B = 1;   // slots per load / write-back batch (4 measured slower: 12.1 vs 10.7 ms at n = 2048)
+constexpr int CH_DONE = 1 << 30;
+
+__device__ inline cplx* ring_col(cplx* ring, int c) { return ring + (size_t)(c & (CH_RING - 1)) * LDB; }
+
+__global__ void __launch_bounds__(CH_NT, 1) band_chase2_kernel(int n, cplx* __restrict__ Bd, cplx* __restrict__ RV, int KS,
+                                                              double* __restrict__ dd, double* __restrict__ ee,
+                                                              int* gprog) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx* ring = reinterpret_cast<cplx*>(smraw);
+  __shared__ volatile int s_loaded, s_done;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane & 7, g4 = lane >> 3;  // window column / row group of the lane
+  const int NG = (n - 1 + CH_W - 1) / CH_W;
+  for (int grp = blockIdx.x; grp < NG; grp += gridDim.x) {
+    const int s0 = grp * CH_W;
+    const int nact = min(CH_W, n - 1 - s0);  // sweeps s0 .. s0 + nact - 1 (<= n - 2)
+    const int wl = nact - 1, sl = s0 + wl;
+    const int KsL = (n - 1 - sl + SB - 1) / SB;
+    const int Tend = 2 * wl + KsL;
+    if (threadIdx.x == 0) {
+      s_loaded = 0;
+      s_done = 0;
+    }
+    __syncthreads();
+    if (warp == CH_W) {
+      // ------------------------------ loader / write-back warp ------------------------------
+      int Tl = 0, Tw = 0;
+      int wb = sl + 1;  // columns < wb need no write-back (nobody reads the group's own columns again)
+      auto need_excl = [&](int T) { return min(n, s0 + 9 + 8 * T); };
+      auto copy_in = [&](int lo, int hi) {
+        for (int e = lo * LDB + lane; e < hi * LDB; e += 32) {
+          const int col = e / LDB, d = e % LDB;
+          ring_col(ring, col)[d] = ldcg_c(Bd + (long)col * LDB + d);
+        }
+      };
+      auto copy_out = [&](int lo, int hi) {
+        for (int e = lo * LDB + lane; e < hi * LDB; e += 32) {
+          const int col = e / LDB, d = e % LDB;
+          Bd[(long)col * LDB + d] = ring_col(ring, col)[d];
+        }
+      };
+      // loads and write-backs are issued for CH_B slots at a time: every batch costs a few dependent L2 round trips
+      // (progress counter, columns, release), which a one-slot batch would put on the compute warps' critical path
+      while (Tw < Tend) {
+        const int done = s_done;
+        bool progressed = false;
+        if (Tl < Tend && Tl <= done + CH_L) {
+          const int Tn = min(Tend, Tl + CH_B);  // load the columns of slots Tl .. Tn-1
+          const int lo = (Tl == 0) ? s0 : need_excl(Tl - 1), hi = need_excl(Tn - 1);
+          bool ready = true;
+          if (hi > lo && grp > 0) {
+            // the previous group's last sweep is s0 - 1: columns < s0 + 8 F are final after F of its steps.  Relaxed
+            // poll (an acquire load costs an L1 invalidation per attempt); the columns themselves are read with
+            // ld.cg from L2, behind the control dependency on the polled value
+            const int req = max(1, (hi - s0 + 7) / 8);
+            int v = 0;
+            if (lane == 0) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(gprog + grp - 1) : "memory");
+            v = __shfl_sync(0xffffffffu, v, 0);
+            ready = v >= req;
+          }
+          if (ready) {
+            if (hi > lo) copy_in(lo, hi);
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) s_loaded = Tn;
+            Tl = Tn;
+            progressed = true;
+          }
+        }
+        if (Tw < done && (done - Tw >= CH_B || done == Tend)) {
+          const int kL = (done - 1) - 2 * wl;  // steps the last sweep has completed: kL + 1
+          if (kL >= 0) {
+            const int cfin = min(n, sl + 1 + 8 * (kL + 1));
+            if (cfin > wb) {
+              copy_out(wb, cfin);
+              wb = cfin;
+            }
+            __syncwarp();
+            if (lane == 0) {
+              const int val = kL + 1;
+              asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gprog + grp), "r"(val) : "memory");
+            }
+          }
+          Tw = done;
+          progressed = true;
+        }
+        if (!progressed) __nanosleep(40);
+      }
+      {
+        const int top = need_excl(Tend - 1);
+        if (top > wb) copy_out(wb, top);
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(gprog + grp), "r"(CH_DONE) : "memory");
+      }
+    } else {
+      // ------------------------------ compute warps: one sweep each ------------------------------
+      const int w = warp;
+      const int s = s0 + w;
+      const bool active = w < nact;
+      const int Ks = active ? (n - 1 - s + SB - 1) / SB : 0;
+      cplx vc = mk(0, 0), tau = mk(0, 0);
+      cplx vr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) vr[i] = mk(0, 0);
+      for (int T = 0; T < Tend; ++T) {
+        if (w == 0) {  // the newest columns are only touched by the first sweep
+          if (lane == 0)
+            while (s_loaded <= T) {
+            }
+          __syncwarp();
+          __threadfence_block();
+        }
+        const int k = T - 2 * w;
+        if (active && k >= 0 && k < Ks) {
+          const int r0 = s + 1 + SB * k;
+          if (k == 0) {
+            cplx* col = ring_col(ring, s);
+            const cplx xc = (r0 + c < n) ? col[1 + c] : mk(0, 0);
+            cplx xr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * (g4 & 1) + i;
+              xr[i] = (r0 + j < n) ? col[1 + j] : mk(0, 0);
+            }
+            double xn2 = (c >= 1) ? cabs2(xc) : 0.0;
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 1);
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 2);
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 4);
+            xn2 = __shfl_sync(0xffffffffu, xn2, 0);
+            const cplx alpha = shfl_c(xc, 0);
+            double beta;
+            cplx scal;
+            larfg(alpha, xn2, beta, tau, scal);
+            vc = (c == 0) ? mk(1, 0) : cmul(xc, scal);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vr[i] = (4 * (g4 & 1) + i == 0) ? mk(1, 0) : cmul(xr[i], scal);
+            if (lane == 0) {
+              ee[s] = beta;
+              dd[s] = col[0].x;
+            }
+            __syncwarp();
+            if (lane < SB && r0 + lane < n) col[1 + lane] = (lane == 0) ? mk(beta, 0) : mk(0, 0);
+          }
+          // ---- load the window (rows r0 .. r0+15, columns r0 .. r0+7) from the ring ----
+          cplx wv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = 4 * g4 + i;
+            const int rg = r0 + r, cgl = r0 + c;
+            cplx x = mk(0, 0);
+            if (rg < n && cgl < n) {
+              if (r >= c)
+                x = ring_col(ring, cgl)[r - c];
+              else
+                x = cconj(ring_col(ring, rg)[c - r]);
+            }
+            wv[i] = x;
+          }
+          {
+            cplx* rv = RV + ((long)s * KS + k) * 9;
+            if (lane < SB) rv[lane] = vc;
+            if (lane == SB) rv[SB] = tau;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // W <- W H
+            cplx z = cmul(wv[i], vc);
+            z = cadd(z, shfl_xor_c(z, 1));
+            z = cadd(z, shfl_xor_c(z, 2));
+            z = cadd(z, shfl_xor_c(z, 4));
+            cfms(wv[i], cmul(tau, z), cconj(vc));
+          }
+          {  // D <- H^H D
+            cplx y = mk(0, 0);
+            if (g4 < 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cfma_conj(y, vr[i], wv[i]);
+            }
+            y = cadd(y, shfl_xor_c(y, 8));
+            if (g4 < 2) {
+              const cplx ty = cmul(cconj(tau), y);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cfms(wv[i], vr[i], ty);
+            }
+          }
+          const bool hasE = (r0 + SB < n);
+          cplx vc2 = mk(0, 0), tau2 = mk(0, 0);
+          cplx vr2[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) vr2[i] = mk(0, 0);
+          if (hasE) {
+            cplx xc = mk(0, 0);
+            cplx xr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const cplx t = shfl_c(wv[i], 16 + 8 * (c >> 2));
+              if ((c & 3) == i) xc = t;
+              xr[i] = shfl_c(wv[i], 16 + 8 * (g4 & 1));
+            }
+            double xn2 = (c >= 1) ? cabs2(xc) : 0.0;
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 1);
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 2);
+            xn2 += __shfl_xor_sync(0xffffffffu, xn2, 4);
+            xn2 = __shfl_sync(0xffffffffu, xn2, 0);
+            const cplx alpha = shfl_c(xc, 0);
+            double beta2;
+            cplx scal;
+            larfg(alpha, xn2, beta2, tau2, scal);
+            vc2 = (c == 0) ? mk(1, 0) : cmul(xc, scal);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) vr2[i] = (4 * (g4 & 1) + i == 0) ? mk(1, 0) : cmul(xr[i], scal);
+            cplx y = mk(0, 0);
+            if (g4 >= 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cfma_conj(y, vr2[i], wv[i]);
+            }
+            y = cadd(y, shfl_xor_c(y, 8));
+            if (g4 >= 2) {
+              const cplx ty = cmul(cconj(tau2), y);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) cfms(wv[i], vr2[i], ty);
+              if (c == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) wv[i] = (g4 == 2 && i == 0) ? mk(beta2, 0) : mk(0, 0);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {  // store the lower part of the window
+            const int r = 4 * g4 + i;
+            const int rg = r0 + r, cgl = r0 + c;
+            if (rg < n && cgl < n && r >= c) {
+              cplx x = wv[i];
+              if (r == c) x.y = 0.0;
+              ring_col(ring, cgl)[r - c] = x;
+            }
+          }
+          vc = vc2;
+          tau = tau2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) vr[i] = vr2[i];
+          if (s == n - 2 && k + 1 == Ks) {
+            __syncwarp();
+            if (lane == 0) dd[n - 1] = ring_col(ring, n - 1)[0].x;
+          }
+        }
+        // end of the slot: every sweep of the group has finished its step
+        asm volatile("bar.sync 1, %0;" ::"n"(CH_W * 32) : "memory");
+        if (threadIdx.x == 0) {
+          __threadfence_block();
+          s_done = T + 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // X <- Q2 X for NC columns per CTA held in shared memory.  X(:, col) starts as the real eigenvector Z(:, perm[col]) of the
 // tridiagonal matrix.  Shared layout: row r of local column q at  q*npad + (r & 7)*(npad/8) + (r >> 3)  so that the
 // threads of a warp (consecutive reflectors = row offsets 8 apart) touch consecutive addresses.
@@ -832,6 +1111,110 @@ __global__ void __launch_bounds__(Q2_NT) q2_apply_kernel(int n, int k, int NC, c
     for (int r = tid; r < n; r += blockDim.x) U[(long)(col0 + q) * ldu + r] = X[q * npad + (r & 7) * n8 + (r >> 3)];
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// X <- Q2 X, second version: no CTA-wide barrier.  Thread k owns the reflectors (s, k) of ALL sweeps (rows s+1+8k ..);
+// reflector (s-1, k) touches rows written by (s, k) (same thread) and by (s, k-1) (left neighbour) only, so the lanes
+// of a warp advance sweep by sweep with __syncwarp and a warp follows its left neighbour warp through one progress
+// word in shared memory.  The NC columns of the tile are processed two at a time for instruction-level parallelism;
+// the reflector of the next sweep is prefetched from L2 into registers.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(288) q2_apply2_kernel(int n, int k, int NC, const double* __restrict__ Z, long ldz,
+                                                        const int* __restrict__ perm, const cplx* __restrict__ RV, int KS,
+                                                        cplx* __restrict__ U, long ldu) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx* X = reinterpret_cast<cplx*>(smraw);
+  const int npad = (n + 7) & ~7;
+  const int n8 = npad >> 3;
+  volatile int* wprog = reinterpret_cast<volatile int*>(X + (size_t)NC * npad);
+  const int col0 = blockIdx.x * NC;
+  const int nc = min(NC, k - col0);
+  if (nc <= 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = 0; q < nc; ++q) {
+    const double* zc = Z + (long)(perm ? perm[col0 + q] : col0 + q) * ldz;
+    for (int r = tid; r < npad; r += blockDim.x)
+      X[q * npad + (r & 7) * n8 + (r >> 3)] = (r < n) ? mk(zc[r], 0.0) : mk(0, 0);
+  }
+  if (tid < (int)(blockDim.x >> 5)) wprog[tid] = n - 1;  // "no sweep done yet" (sweeps run from n-2 down to 0)
+  __syncthreads();
+  const int kk = tid;  // reflector index of this thread
+  // prefetch the reflector of the first sweep in which this thread is active
+  cplx v[SB], vn[SB];
+  cplx tau = mk(0, 0), taun = mk(0, 0);
+  auto fetch = [&](int s, cplx (&vv)[SB], cplx& tt) {
+    const int Ks = (n - 1 - s + SB - 1) / SB;
+    if (s >= 0 && kk < Ks) {
+      const cplx* rv = RV + ((long)s * KS + kk) * 9;
+#pragma unroll
+      for (int i = 0; i < SB; ++i) vv[i] = ldcg_c(rv + i);
+      tt = ldcg_c(rv + SB);
+    } else {
+      tt = mk(0, 0);
+    }
+  };
+  fetch(n - 2, vn, taun);
+  for (int s = n - 2; s >= 0; --s) {
+#pragma unroll
+    for (int i = 0; i < SB; ++i) v[i] = vn[i];
+    tau = taun;
+    fetch(s - 1, vn, taun);  // in flight while this sweep is applied
+    if (warp > 0) {           // the left neighbour warp must have finished sweep s+1
+      if (lane == 0)
+        while (wprog[warp - 1] > s + 1) {
+        }
+      __syncwarp();
+      __threadfence_block();
+    }
+    const int Ks = (n - 1 - s + SB - 1) / SB;
+    if (kk < Ks && !(tau.x == 0.0 && tau.y == 0.0)) {
+      const int r0 = s + 1 + SB * kk;
+      int off[SB];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) off[i] = ((r0 + i) & 7) * n8 + ((r0 + i) >> 3);  // rows past n carry v = 0
+      for (int q = 0; q < nc; q += 2) {
+        const bool hb = q + 1 < nc;
+        cplx* xa = X + q * npad;
+        cplx* xb = X + (hb ? q + 1 : q) * npad;
+        cplx a[SB], b[SB];
+        cplx da0 = mk(0, 0), da1 = mk(0, 0), db0 = mk(0, 0), db1 = mk(0, 0);
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+          const bool in = r0 + i < npad;
+          a[i] = in ? xa[off[i]] : mk(0, 0);
+          b[i] = (in && hb) ? xb[off[i]] : mk(0, 0);
+        }
+#pragma unroll
+        for (int i = 0; i < SB; i += 2) {
+          cfma_conj(da0, v[i], a[i]);
+          cfma_conj(da1, v[i + 1], a[i + 1]);
+          cfma_conj(db0, v[i], b[i]);
+          cfma_conj(db1, v[i + 1], b[i + 1]);
+        }
+        const cplx tda = cmul(tau, cadd(da0, da1));
+        const cplx tdb = cmul(tau, cadd(db0, db1));
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+          const bool in = r0 + i < npad;
+          cfms(a[i], v[i], tda);
+          if (in) xa[off[i]] = a[i];
+          if (hb) {
+            cfms(b[i], v[i], tdb);
+            if (in) xb[off[i]] = b[i];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      wprog[warp] = s;
+    }
+  }
+  __syncthreads();
+  for (int q = 0; q < nc; ++q)
+    for (int r = tid; r < n; r += blockDim.x) U[(long)(col0 + q) * ldu + r] = X[q * npad + (r & 7) * n8 + (r >> 3)];
+}
+
 }  // namespace
 
 #ifdef TEVO_SBR_TIMING
@@ -916,9 +1299,24 @@ void Sbr::chase(cudaStream_t st, int n, double* d, double* e) {
     // d[0] = B(0,0): handled by the caller (no sweep exists)
     return;
   }
-  int ctas = std::min(16, std::max(1, (n - 1 + 7) / 8));
+  static const int chase_version = [] {
+    const char* e = getenv("TEVO_SBR_CHASE");  // 1: one warp per sweep with hand-offs through L2; 2: lock-step groups
+    return e ? atoi(e) : 2;
+  }();
   void* args[] = {(void*)&n, (void*)&Bd_, (void*)&RV_, (void*)&KS, (void*)&d, (void*)&e, (void*)&prog_};
-  TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)band_chase_kernel, dim3(ctas), dim3(256), args, 0, st));
+  if (chase_version == 1) {
+    int ctas = std::min(16, std::max(1, (n - 1 + 7) / 8));
+    TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)band_chase_kernel, dim3(ctas), dim3(256), args, 0, st));
+  } else {
+    const size_t ring_bytes = sizeof(cplx) * (size_t)CH_RING * LDB;
+    static PerDeviceOnce once;
+    once([&]() {
+      TEVO_CUDA_CHECK(cudaFuncSetAttribute(band_chase2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+    });
+    const int ngroups = (n - 1 + CH_W - 1) / CH_W;
+    const int ctas = std::max(1, std::min(8, ngroups));
+    TEVO_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)band_chase2_kernel, dim3(ctas), dim3(CH_NT), args, ring_bytes, st));
+  }
   TEVO_LAUNCHED();
 }
 
@@ -930,8 +1328,28 @@ void Sbr::apply_q2(cudaStream_t st, int n, int k, const double* Z, long ldz, con
   });
   const int npad = (n + 7) & ~7;
   const size_t per_col = (size_t)npad * sizeof(cplx);
-  const size_t rv_bytes = (size_t)2 * ks_ * 9 * sizeof(cplx);  // reflectors of two sweeps (double buffer)
   const size_t budget = (size_t)227 * 1024;
+  static const int q2_version = [] {
+    const char* e = getenv("TEVO_SBR_Q2");  // 1: one CTA barrier per sweep (default); 2: warp-pipelined (measured slower)
+    return e ? atoi(e) : 1;
+  }();
+  if (q2_version != 1 && ks_ <= 288) {
+    const int threads = 32 * ((ks_ + 31) / 32);
+    const size_t extra = 64 * sizeof(int);
+    if (per_col + extra > budget) throw TevoError(1, "sbr: matrix too large for the shared-memory back-transformation");
+    const int ncmax = (int)((budget - extra) / per_col);
+    const int waves = std::max(1, (k + ncmax * num_sms_ - 1) / (ncmax * num_sms_));
+    const int NC = std::min(ncmax, std::max(1, (k + waves * num_sms_ - 1) / (waves * num_sms_)));
+    const int grid = (k + NC - 1) / NC;
+    static PerDeviceOnce once2;
+    once2([&]() {
+      TEVO_CUDA_CHECK(cudaFuncSetAttribute(q2_apply2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    });
+    q2_apply2_kernel<<<grid, threads, (size_t)NC * per_col + extra, st>>>(n, k, NC, Z, ldz, perm_dev, RV_, ks_, U, ldu);
+    TEVO_LAUNCHED();
+    return;
+  }
+  const size_t rv_bytes = (size_t)2 * ks_ * 9 * sizeof(cplx);  // reflectors of two sweeps (double buffer)
   if (rv_bytes + per_col > budget) throw TevoError(1, "sbr: matrix too large for the shared-memory back-transformation");
   const int ncmax = (int)((budget - rv_bytes) / per_col);
   // as many columns per CTA as fit, but no more than an even split of the k columns over whole waves of CTAs needs

@@ -156,8 +156,12 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
 
   const int nk = (K + BK - 1) / BK;
   __shared__ unsigned long long full_bar[STAGES];
-  const bool bulk = BULK && (m0 + BM <= M) && (n0 + BN <= N) && (K % BK == 0);
-  constexpr unsigned STAGE_BYTES = (unsigned)((BM + BN) * BK * sizeof(cplx));
+  // operands whose tile rows are long contiguous runs (m- / n-contiguous: 2 KB / 1 KB per k) go through the TMA
+  // engine; k-contiguous operands (256-byte runs) stay on cp.async, where bulk copies measured slower
+  const bool interior = BULK && (m0 + BM <= M) && (n0 + BN <= N) && (K % BK == 0);
+  const bool bulkA = interior && !A_KMAJOR, bulkB = interior && !B_KMAJOR;
+  const bool bulk = bulkA || bulkB;
+  const unsigned stage_bytes = (unsigned)(((bulkA ? BM : 0) + (bulkB ? BN : 0)) * BK * sizeof(cplx));
   if (bulk) {
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -166,49 +170,33 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
     }
     __syncthreads();
   }
-  // fills stage st with k-tile nx (warp 0 issues; the stage was last read before the preceding CTA barrier)
-  auto bulk_fill = [&](int st, int nx) {
-    if (warp == 0) {
+  // fills stage st with k-tile nx (bulk part: warp 0 issues; the stage was last read before the preceding CTA barrier)
+  auto fill = [&](int st, int nx) {
+    if (bulk && warp == 0) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      if (lane == 0) mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+      if (lane == 0) mbar_expect_tx(&full_bar[st], stage_bytes);
       __syncwarp();
-      bulk_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, &full_bar[st], lane);
-      bulk_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, &full_bar[st], lane);
+      if (bulkA) bulk_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, &full_bar[st], lane);
+      if (bulkB) bulk_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, &full_bar[st], lane);
     }
+    if (!bulkA) load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
+    if (!bulkB) load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
   };
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) {
-      if (bulk) {
-        bulk_fill(s, s);
-      } else {
-        load_tile<BM, A_KMAJOR>(sA + s * TA::elems, A, lda, m0, s * BK, M, K);
-        load_tile<BN, B_KMAJOR>(sB + s * TB::elems, B, ldb, n0, s * BK, N, K);
-      }
-    }
-    if (!bulk) cp_async_commit();
+    if (s < nk) fill(s, s);
+    cp_async_commit();
   }
 
   const double sa = conjA ? -1.0 : 1.0, sb = conjB ? -1.0 : 1.0;
   for (int kt = 0; kt < nk; ++kt) {
-    if (bulk) {
-      mbar_wait(&full_bar[kt % STAGES], (unsigned)((kt / STAGES) & 1));
-    } else {
-      cp_async_wait<STAGES - 2>();
-    }
+    cp_async_wait<STAGES - 2>();
+    if (bulk) mbar_wait(&full_bar[kt % STAGES], (unsigned)((kt / STAGES) & 1));
     __syncthreads();
     {
       const int nx = kt + STAGES - 1;
-      if (nx < nk) {
-        const int st = nx % STAGES;
-        if (bulk) {
-          bulk_fill(st, nx);
-        } else {
-          load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
-          load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
-        }
-      }
-      if (!bulk) cp_async_commit();
+      if (nx < nk) fill(nx % STAGES, nx);
+      cp_async_commit();
     }
     const cplx* a_s = sA + (kt % STAGES) * TA::elems;
     const cplx* b_s = sB + (kt % STAGES) * TB::elems;
@@ -246,7 +234,7 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
         for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
     }
   }
-  if (!bulk) cp_async_wait<0>();
+  cp_async_wait<0>();
 
   const bool has_beta = (beta.x != 0.0 || beta.y != 0.0);
 #pragma unroll
@@ -291,7 +279,7 @@ void launch_cb(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, 
 int zgemm_bulk_default() {
   static const int v = [] {
     const char* e = getenv("TEVO_ZGEMM_BULK");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 1;
   }();
   return v;
 }
@@ -312,7 +300,12 @@ template <bool AK, bool BK_>
 void launch(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
             long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits = 1, int Kc = 0, long part_stride = 0,
             int batch = 1, long bsA = 0, long bsB = 0, long bsC = 0, int lower_only = 0) {
-  static const bool ctsign = getenv("TEVO_ZGEMM_CTSIGN") != nullptr;
+  // compile-time conjugation signs (fold into DMMA operand modifiers): +4.6 % at the theta shape, tests green on the
+  // B200 (profiles/r02_checks.log); TEVO_ZGEMM_CTSIGN=0 selects the run-time-sign instantiation
+  static const bool ctsign = [] {
+    const char* e = getenv("TEVO_ZGEMM_CTSIGN");
+    return e ? atoi(e) != 0 : true;
+  }();
 #define TEVO_ZG_ARGS st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc, part_stride, batch, bsA, \
                      bsB, bsC, lower_only
   if (!ctsign) {

@@ -12,7 +12,8 @@ import tevo_b200 as t
 ctx = default_ctx()
 lib = load()
 lib.tevo_debug_set_heig_mode(2)   # the two-stage reduction is opt-in
-names = ["mini-phase", "barrier a", "panel QR (CTA 0)", "barrier b", "pass: tiles", "pass: flush", "barrier c"]
+names = ["mini-phase", "barrier a", "panel QR (CTA 0)", "barrier b", "pass: tiles", "pass: flush", "barrier c", "-",
+         "QR: load panel", "QR: 8 columns", "QR: T factor / taus", "QR: write V, band"]
 out = (C.c_ulonglong * 16)()
 PD = C.POINTER(C.c_double)
 for n in [int(x) for x in sys.argv[1:]]:
