@@ -43,8 +43,10 @@ def test_extreme_truncation_keywords(tevo, oracle, kw):
         ospec = oracle.apply_gate(o, g, **kw)
         spec = tevo.apply_gate(p, tevo.BondGate(g.G, b), **kw)
         assert len(spec) == len(ospec.eigs), (b, kw)
-        np.testing.assert_allclose(spec.eigs, ospec.eigs, rtol=1e-9, atol=1e-15)
-        assert abs(spec.truncerr - ospec.truncerr) <= 1e-9 * ospec.truncerr + 1e-15
+        # north-star tolerance 1e-10 on the weights; the absolute floor covers weights below ~1e-5 of the largest,
+        # which the density-matrix route resolves absolutely
+        np.testing.assert_allclose(spec.eigs, ospec.eigs, rtol=1e-10, atol=1e-15)
+        assert abs(spec.truncerr - ospec.truncerr) <= 1e-10 * ospec.truncerr + 1e-15
     _compare(tevo, oracle, o, p)
 
 
