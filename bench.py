@@ -327,7 +327,7 @@ def run_sharded(args):
     import torch
     import tevo_b200 as t
     from timeevomps_jl_b200 import replicas
-    from timeevomps_jl_b200.sharded import DeviceSegment, ShardedTEBD, segment_bounds
+    from timeevomps_jl_b200.sharded import DeviceSegment, ShardedTEBD, weighted_segment_bounds
     budget = Budget(args.budget)
     rank, world, local = replicas.world()
     torch.cuda.set_device(local)
@@ -338,9 +338,11 @@ def run_sharded(args):
     ctx = t.default_ctx()
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
     N, chi = args.nsites, args.chi
-    lo, hi = segment_bounds(N, world, rank)
+    # contiguous segments of equal estimated cost (~ chi_j^3 per site: the chain ends carry small bonds)
+    wts = [float(min(chi, 2 ** min(j + 1, N - j - 1, 40))) ** 3 for j in range(N)]
+    lo, hi = weighted_segment_bounds(wts, world, rank)
     seg = DeviceSegment.random(N, chi, lo, hi, ghost=(rank < world - 1), seed=0)
-    sh = ShardedTEBD(seg, N, dist, rank, world, device="cuda")
+    sh = ShardedTEBD(seg, N, dist, rank, world, device="cuda", bounds=(lo, hi))
     Ustart, Us, Uend = t.time_evo_gates(args.dt, t.gates(model_bondop(t, args.model, N)), t.TEBD4())
     kw = dict(maxdim=chi, mindim=chi)
 
@@ -450,6 +452,7 @@ def run_sharded(args):
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
         "fp64_tensor": {"algorithmic_tflops": flops_step / (ms_per_step * 1e-3) / 1e12, "peak_tflops": zpeak * world,
                         "frac": flops_step / (ms_per_step * 1e-3) / 1e12 / (zpeak * world)},
+        "segment_rank0": [int(lo), int(hi)],
         "boundary_bytes_sent_per_step_rank0": bytes_per_step,
         "boundary_exchange_ms_per_step_max_rank": exch_ms,
         "boundary_transfer_ms_per_step_at_770GBs": bytes_per_step / 770e9 * 1e3,
@@ -704,8 +707,9 @@ def run_sequential(args):
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version there)
+    # keep stdout to the one JSON line: NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to stdout unless told
+    # otherwise
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args)
         return

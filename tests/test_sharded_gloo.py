@@ -110,3 +110,22 @@ def test_segment_bounds_cover_chain():
             cover += list(range(lo, hi))
         assert cover == list(range(N))
         assert owner_of_site(N, world, 0) == 0 and owner_of_site(N, world, N - 1) == world - 1
+
+
+def test_weighted_segment_bounds_cover_the_chain():
+    """The benchmark's cost-weighted partition: contiguous, covering, at least two sites per rank, and balancing the
+    estimated cost (the chain ends of a saturated MPS are cheap, so the edge ranks take more sites)."""
+    import tevo_b200  # noqa: F401  (registers the package alias)
+    from timeevomps_jl_b200.sharded import weighted_segment_bounds
+    N, chi = 256, 1024
+    w = [float(min(chi, 2 ** min(j + 1, N - j - 1, 40))) ** 3 for j in range(N)]
+    for world in (1, 2, 3, 4, 8):
+        b = [weighted_segment_bounds(w, world, r) for r in range(world)]
+        assert b[0][0] == 0 and b[-1][1] == N
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(hi - lo >= 2 for lo, hi in b)
+        cost = [sum(w[lo:hi]) for lo, hi in b]
+        assert max(cost) <= 1.08 * (sum(w) / world)
+    b8 = [weighted_segment_bounds(w, 8, r) for r in range(8)]
+    assert b8[0][1] - b8[0][0] > b8[3][1] - b8[3][0]            # edge ranks hold more sites than interior ranks
+    assert [weighted_segment_bounds([1.0] * 4, 2, r) for r in range(2)] == [(0, 2), (2, 4)]

@@ -23,6 +23,28 @@ def segment_bounds(N: int, world: int, rank: int) -> Tuple[int, int]:
     return (rank * N) // world, ((rank + 1) * N) // world
 
 
+def weighted_segment_bounds(weights: Sequence[float], world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous partition of the sites with (nearly) equal total weight per rank.  Used by the benchmark with
+    weight_j ~ chi_j^3 (the cost of a two-site update next to site j): the first and last ~log_d(chi) sites of a
+    saturated chain carry small bond dimensions, so the edge ranks take a few more sites than the interior ones.
+    Every rank gets at least two sites."""
+    N = len(weights)
+    tot = float(sum(weights))
+    cuts = [0]
+    acc, j = 0.0, 0
+    for r in range(1, world):
+        target = tot * r / world
+        while j < N and acc + weights[j] * 0.5 < target:
+            acc += weights[j]
+            j += 1
+        j = max(j, cuts[-1] + 2)
+        j = min(j, N - 2 * (world - r))
+        cuts.append(j)
+        acc = float(sum(weights[:j]))
+    cuts.append(N)
+    return cuts[rank], cuts[rank + 1]
+
+
 def owner_of_site(N: int, world: int, j: int) -> int:
     for r in range(world):
         lo, hi = segment_bounds(N, world, r)
@@ -58,34 +80,60 @@ class Segment:
 
 
 class ShardedTEBD:
-    def __init__(self, segment: Segment, N: int, dist, rank: int, world: int, device="cpu"):
+    def __init__(self, segment: Segment, N: int, dist, rank: int, world: int, device="cpu", bounds=None):
         self.seg, self.N, self.dist, self.rank, self.world, self.device = segment, N, dist, rank, world, device
-        self.lo, self.hi = segment_bounds(N, world, rank)
+        self.lo, self.hi = bounds if bounds is not None else segment_bounds(N, world, rank)
         self.nloc = self.hi - self.lo
         self.bytes_sent = 0
         self.exchange_s = 0.0     # host wall time spent in the boundary exchange (sends, receives, their syncs)
 
     # ---- point-to-point helpers ----
-    def _send(self, t, shape, dst):
+    def _exchange(self, send, recv_from):
+        """One batched neighbour exchange: `send` = (dst, [tensors]) or None, `recv_from` = src rank or None.  Two
+        rounds of batch_isend_irecv (sizes, then payload), so that a rank's send and receive are posted together:
+        with blocking send-then-recv the transfers of a layer form a serial chain from the last rank to the first.
+        Returns the list of received float64 tensors (same split as the sender's list)."""
         import torch
-        hdr = torch.tensor(list(shape) + [0] * (3 - len(shape)), dtype=torch.int64, device=self.device)
-        self.dist.send(hdr, dst)
-        self.dist.send(t.contiguous(), dst)
-        self.bytes_sent += t.numel() * t.element_size()
-
-    def _recv(self, src, dtype_elems_per_entry=2):
-        import torch
-        hdr = torch.zeros(3, dtype=torch.int64, device=self.device)
-        self.dist.recv(hdr, src)
-        shape = tuple(int(x) for x in hdr.tolist() if int(x) > 0)
-        n = int(np.prod(shape)) * dtype_elems_per_entry
-        t = torch.empty(n, dtype=torch.float64, device=self.device)
-        self.dist.recv(t, src)
-        return t, shape
+        dist = self.dist
+        NH = 8
+        ops, hdr_in = [], None
+        if send is not None:
+            dst, parts = send
+            sizes = [int(p.numel()) for p in parts]
+            hdr = torch.tensor([len(parts)] + sizes + [0] * (NH - 1 - len(sizes)), dtype=torch.int64, device=self.device)
+            ops.append(dist.P2POp(dist.isend, hdr, dst))
+        if recv_from is not None:
+            hdr_in = torch.zeros(NH, dtype=torch.int64, device=self.device)
+            ops.append(dist.P2POp(dist.irecv, hdr_in, recv_from))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        ops, buf, sizes_in = [], None, []
+        if send is not None:
+            dst, parts = send
+            payload = torch.cat([p.reshape(-1).to(torch.float64) for p in parts]) if len(parts) > 1 else parts[0].reshape(-1)
+            payload = payload.contiguous()
+            ops.append(dist.P2POp(dist.isend, payload, dst))
+            self.bytes_sent += payload.numel() * payload.element_size()
+        if recv_from is not None:
+            h = hdr_in.tolist()
+            sizes_in = [int(x) for x in h[1:1 + int(h[0])]]
+            buf = torch.empty(sum(sizes_in), dtype=torch.float64, device=self.device)
+            ops.append(dist.P2POp(dist.irecv, buf, recv_from))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        if buf is None:
+            return []
+        out, o = [], 0
+        for n in sizes_in:
+            out.append(buf[o:o + n])
+            o += n
+        return out
 
     # ---- one Trotter layer ----
     def apply_layer(self, gates: Sequence, **kw):
         """gates: BondGate-like objects with global bond .b and matrix .G, all on disjoint bonds."""
+        import time as _time
+        import torch
         bonds = sorted(g.b for g in gates)
         if any(b2 - b1 < 2 for b1, b2 in zip(bonds, bonds[1:])):
             # e.g. a TEBD2Sweep layer (all bonds): the cut gate would read a ghost copy of a site that the right
@@ -97,32 +145,35 @@ class ShardedTEBD:
         left_cut = self.lo - 1           # bond (lo-1 | lo), owned by rank-1
         has_right = self.rank < self.world - 1 and any(g.b == right_cut for g in gates)
         has_left = self.rank > 0 and any(g.b == left_cut for g in gates)
-        import time as _time
         self.seg.sync()
         _t0 = _time.perf_counter()
         # 1. boundary tensors travel left: my first site goes to the rank that updates the cut bond
-        if has_left:
-            t, shape = self.seg.site_tensor(0)
-            self._send(t, shape, self.rank - 1)
-        if has_right:
-            t, shape = self._recv(self.rank + 1)
-            self.seg.set_site_tensor(self.nloc, t, shape)
+        if has_left or has_right:
+            send = None
+            if has_left:
+                t, shape = self.seg.site_tensor(0)
+                send = (self.rank - 1, [torch.tensor(list(shape) + [0], dtype=torch.float64, device=self.device), t])
+            got = self._exchange(send, self.rank + 1 if has_right else None)
+            if has_right:
+                shape = tuple(int(x) for x in got[0].tolist()[:3])   # (header padded to 32 bytes: payload stays aligned)
+                self.seg.set_site_tensor(self.nloc, got[1], shape)
         self.exchange_s += _time.perf_counter() - _t0
         # 2. local updates (all independent)
         out = self.seg.apply_layer([(g.b - self.lo, g.G) for g in mine], **kw)
         self.seg.sync()
         _t0 = _time.perf_counter()
         # 3. updated boundary tensor and cut-bond Schmidt values travel back right
-        if has_right:
-            t, shape = self.seg.site_tensor(self.nloc)
-            self._send(t, shape, self.rank + 1)
-            lt = self.seg.lam_tensor(self.nloc)
-            self._send(lt, (lt.numel(),), self.rank + 1)
-        if has_left:
-            t, shape = self._recv(self.rank - 1)
-            self.seg.set_site_tensor(0, t, shape)
-            lt, lshape = self._recv(self.rank - 1, dtype_elems_per_entry=1)
-            self.seg.set_lam_tensor(0, lt)
+        if has_left or has_right:
+            send = None
+            if has_right:
+                t, shape = self.seg.site_tensor(self.nloc)
+                lt = self.seg.lam_tensor(self.nloc)
+                send = (self.rank + 1, [torch.tensor(list(shape) + [0], dtype=torch.float64, device=self.device), t, lt])
+            got = self._exchange(send, self.rank - 1 if has_left else None)
+            if has_left:
+                shape = tuple(int(x) for x in got[0].tolist()[:3])
+                self.seg.set_site_tensor(0, got[1], shape)
+                self.seg.set_lam_tensor(0, got[2])
         self.exchange_s += _time.perf_counter() - _t0
         return out
 
