@@ -134,3 +134,20 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out[0] == "6" and "libtevo" in out[1:]
+
+
+def test_julia_shim_only_binds_declared_symbols():
+    """The Julia shim cannot be executed here (no Julia in the image); at least every symbol it `ccall`s must be
+    declared in include/tevo.h and exported by the built library, and the two drop-in drivers must exist."""
+    import re
+    shim = open(os.path.join(ROOT, "timeevomps.jl_b200", "julia", "TevoB200.jl")).read()
+    header = open(os.path.join(ROOT, "include", "tevo.h")).read()
+    syms = set(re.findall(r"ccall\(\(:(tevo_\w+), LIB\)", shim))
+    assert len(syms) >= 25
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "timeevomps.jl_b200", "libtevo.so"))
+    for s in sorted(syms):
+        assert re.search(r"\b%s\s*\(" % s, header), "%s is not declared in include/tevo.h" % s
+        assert hasattr(lib, s), "%s is not exported by libtevo.so" % s
+    assert re.search(r"^function tebd!\(psi::MPS, H::GateList, dt::Number, tf::Number, alg::TEBDalg=TEBD2\(\)", shim, re.M)
+    assert re.search(r"^function tdvp!\(psi::MPS, H::MPO, dt::Number, tf::Number", shim, re.M)
