@@ -23,6 +23,13 @@ def test_roundtrip_and_inner(tevo, oracle):
     p = _to_dev(tevo, o)
     for a, b in zip(o.A, p.tensors()):
         assert np.array_equal(a, b)
+    # download into caller-owned buffers (the bench's end-to-end path hands pinned host memory here)
+    bufs = [np.empty(a.shape, dtype=np.complex128, order="F") for a in o.A]
+    bufs[3] = np.empty((1, 2, 1), dtype=np.complex128, order="F")      # wrong shape: a fresh array is returned instead
+    outs = p.tensors(out=bufs)
+    for j, (a, b) in enumerate(zip(o.A, outs)):
+        assert np.array_equal(a, b)
+        assert (b is bufs[j]) == (j != 3)
     assert abs(tevo.inner(p, p) - oracle.inner(o, o)) < 1e-13
     o2 = oracle.MPS.random(8, 5, seed=2)
     p2 = _to_dev(tevo, o2)

@@ -121,15 +121,22 @@ class MPS:
         assert t.ndim == 3 and t.shape[1] == self.d
         check(load().tevo_mps_upload_site(self.h, j, t.shape[0], t.shape[2], _addr(t)), self.ctx.h)
 
-    def site(self, j: int) -> np.ndarray:
+    def site(self, j: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Site tensor j as a (chi_l, d, chi_r) column-major array.  `out`: a caller-owned complex128 F-ordered array of
+        that shape (e.g. a view of pinned host memory, which the device copies into directly); a fresh array
+        otherwise (also when the bond dimensions no longer match `out`)."""
         l, r = C.c_int(), C.c_int()
         check(load().tevo_mps_site_dims(self.h, j, C.byref(l), C.byref(r)), self.ctx.h)
-        out = np.empty((l.value, self.d, r.value), dtype=np.complex128, order="F")
+        shape = (l.value, self.d, r.value)
+        if (out is None or out.shape != shape or out.dtype != np.complex128 or not out.flags["F_CONTIGUOUS"]
+                or not out.flags["WRITEABLE"]):
+            out = np.empty(shape, dtype=np.complex128, order="F")
         check(load().tevo_mps_download_site(self.h, j, _addr(out), out.size), self.ctx.h)
         return out
 
-    def tensors(self) -> List[np.ndarray]:
-        return [self.site(j) for j in range(self.N)]
+    def tensors(self, out: Optional[Sequence[np.ndarray]] = None) -> List[np.ndarray]:
+        """All site tensors; `out` (optional) is a list of per-site buffers reused where the shapes still match."""
+        return [self.site(j, None if out is None else out[j]) for j in range(self.N)]
 
     def bond_dims(self) -> List[int]:
         arr = (C.c_int * (self.N - 1))()
