@@ -270,9 +270,28 @@ def panel_roofline(prof, c0, c1, hbm_peak, peak_src, label="tridiag_panel_kernel
                        "kernel cannot reach it by construction of the one-stage algorithm"}
 
 
+_REAL_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write banners there (NCCL prints its version on the first
+    communicator), so file descriptor 1 is pointed at stderr for the duration of the run and `emit` writes the line
+    to the saved descriptor."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
 def emit(line):
-    sys.stdout.write(json.dumps(line) + "\n")
-    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT_FD, data)
 
 
 def run_reference(args):
@@ -702,9 +721,7 @@ def run_sequential(args):
 # ---------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
-    # keep stdout to the one JSON line: NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) to stdout unless told
-    # otherwise
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
