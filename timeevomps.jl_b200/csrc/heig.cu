@@ -673,9 +673,20 @@ void Heig::init() {
   // [barrier counter (one 128-byte line) | acc_yv NREP*2*PW | acc_cw NREP*2*PW*PW | acc_cv NREP*2*PW*PW]
   TEVO_CUDA_CHECK(cudaMalloc(&acc_, sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW)));
   sbr_.init(num_sms_);
+  // second stream: the compact-WY set-up of the back-transformation runs beside the divide & conquer (see factor())
+  TEVO_CUDA_CHECK(cudaStreamCreateWithFlags(&aux_, cudaStreamNonBlocking));
+  TEVO_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  TEVO_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
 }
 
 void Heig::destroy() {
+  if (aux_) {
+    cudaStreamSynchronize(aux_);
+    cudaStreamDestroy(aux_);
+    cudaEventDestroy(ev_fork_);
+    cudaEventDestroy(ev_join_);
+    aux_ = nullptr;
+  }
   stedc_.destroy();
   sbr_.destroy();
   auto fr = [](void* p) {
@@ -730,6 +741,10 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
   });
   if (n > 4096) throw TevoError(1, "heig: n > 4096 not supported");
   g_heig_calls.fetch_add(1, std::memory_order_relaxed);
+  if (wy_pending_) {  // a previous factorisation whose vectors() was never called: its WY set-up still owns the buffers
+    TEVO_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join_, 0));
+    wy_pending_ = false;
+  }
   double* zero_from = acc_;  // the barrier counter and the replicated accumulators are cleared before every panel
   const size_t zero_bytes = sizeof(double) * (16 + NREP * 2 * PW + 2 * NREP * 2 * PW * PW);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);
@@ -845,6 +860,22 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     last_diag_kernel<<<1, 256, 0, st>>>(n, A, lda, d_);
     TEVO_LAUNCHED();
   }
+  // The compact-WY set-up below (T factors, V*T, pair factors: ~0.9 ms of small GEMMs at n = 2048) only needs the
+  // reflectors; the divide & conquer (~3.1 ms of latency-bound stages) only needs d and e, so they can run side by
+  // side (WY work on a second stream, joined by vectors()).  Measured: -3.8 % per sequential TEBD4 step at chi = 1024
+  // (profiles/r02_wy_overlap.log), all sequential tests green - but the layer-parallel mode (several lanes, each with
+  // its own pair of streams) hit an illegal memory access with it that is not understood yet, so it is OFF unless
+  // TEVO_WY_OVERLAP=1 and never used by the lanes.
+  static const bool wy_overlap = [] {
+    const char* e = getenv("TEVO_WY_OVERLAP");
+    return e ? atoi(e) != 0 : false;
+  }();
+  cudaStream_t main_st = st;
+  if (wy_overlap && aux_ && max_ctas_ == 0 && n >= 256) {
+    TEVO_CUDA_CHECK(cudaEventRecord(ev_fork_, main_st));
+    TEVO_CUDA_CHECK(cudaStreamWaitEvent(aux_, ev_fork_, 0));
+    st = aux_;
+  }
   if (tail_t0 >= 0) {
     // the tail kernel keeps no panel dots: V^H V of its panels (the input of the compact-WY factors) by GEMM
     const cplx ONE1 = mk(1, 0), ZERO1 = mk(0, 0);
@@ -891,6 +922,11 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
                     npairs_);
     }
   }
+  if (st != main_st) {
+    TEVO_CUDA_CHECK(cudaEventRecord(ev_join_, st));
+    wy_pending_ = true;
+    st = main_st;
+  }
   {
     ProfScope ps(st, P_STEDC);
     stedc_.run(st, n, d_, e_, evals_, Z_);
@@ -899,6 +935,10 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
 
 void Heig::vectors(cudaStream_t st, const int* perm_dev, int k, cplx* U, long ldu) {
   const int n = n_;
+  if (wy_pending_) {  // join the compact-WY set-up that ran beside the divide & conquer
+    TEVO_CUDA_CHECK(cudaStreamWaitEvent(st, ev_join_, 0));
+    wy_pending_ = false;
+  }
   if (k < 1) return;
   ProfScope ps(st, P_BACK);
   const cplx ONE = mk(1, 0), MONE = mk(-1, 0), ZERO = mk(0, 0);

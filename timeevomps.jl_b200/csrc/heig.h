@@ -38,6 +38,9 @@ class Heig {
   Stedc stedc_;
   Sbr sbr_;                // two-stage reduction (dense -> band -> tridiagonal), opt-in (see factor())
   bool two_stage_ = false;  // which reduction produced the current factorisation
+  cudaStream_t aux_ = nullptr;  // compact-WY set-up beside the divide & conquer
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  bool wy_pending_ = false;
   int num_sms_ = 148;
   int max_ctas_ = 0;
   int cap_ = 0, n_ = 0;
