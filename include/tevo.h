@@ -211,6 +211,13 @@ int tevo_test_heig_ctas(tevo_ctx* ctx, int n, const tevo_complex* A, double* eva
  * d_out (n) / e_out (n-1) the tridiagonal matrix, and optionally x_out (n x k) = Q2 * x_real (n x k real) */
 int tevo_test_sbr(tevo_ctx* ctx, int n, const tevo_complex* A, tevo_complex* band_out, tevo_complex* v_out,
                   tevo_complex* taus_out, double* d_out, double* e_out, int k, const double* x_real, tevo_complex* x_out);
+/* one diagonal-block step of the CholeskyQR factorisation (csrc/cholqr.cu) on host buffers: G (nb x nb, nb <= 64,
+ * column-major, Hermitian positive definite, lower part read) -> L_out = chol(G) (lower, real diagonal), X_out =
+ * inv(L), stats_out[0..1] = smallest / largest pivot (stats_out[0] < 0: not positive definite).  variant 0 = panel
+ * kernel (default), 1 = register-tiled kernel, 2 = shared-memory kernel.  reps > 0: us_out = time per launch over
+ * reps back-to-back launches; cycles_out (8 doubles or NULL): clock64 phase sums of variant 0 */
+int tevo_test_potrf_block(tevo_ctx* ctx, int variant, int nb, const tevo_complex* G, tevo_complex* L_out,
+                          tevo_complex* X_out, double* stats_out, int reps, double* us_out, double* cycles_out);
 /* Hermitian eigensolver variant used by the split (process-wide): 0 = default (one-stage blocked Householder
  * reduction; the two-stage one if the environment sets TEVO_HEIG_TWOSTAGE), 1 = one-stage, 2 = two-stage reduction
  * dense -> band of width 8 -> tridiagonal (n <= 2056; parity-tested, not yet faster: DESIGN.md) */

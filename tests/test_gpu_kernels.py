@@ -194,3 +194,56 @@ def test_heig_hard_spectra(tevo, kind):
     assert np.abs(np.sort(w) - np.sort(s)).max() <= 1e-13 * nrm * n ** 0.5 + 1e-300
     assert np.abs(U.conj().T @ U - np.eye(n)).max() <= 2e-13 * n ** 0.5
     assert np.abs(A @ U - U * w).max() <= 1e-13 * nrm * n + 1e-300
+
+
+def _potrf_block(G, variant, reps=0, cycles=False):
+    from timeevomps_jl_b200._lib import load, check, default_ctx
+    ctx = default_ctx()
+    nb = G.shape[0]
+    Gf = np.asfortranarray(G.astype(np.complex128))
+    L = np.zeros((nb, nb), dtype=np.complex128, order="F")
+    X = np.zeros((nb, nb), dtype=np.complex128, order="F")
+    stats = np.zeros(2)
+    us = C.c_double(0.0)
+    cyc = np.zeros(8)
+    dp = C.POINTER(C.c_double)
+    check(load().tevo_test_potrf_block(ctx.h, variant, nb, Gf.ctypes.data, L.ctypes.data, X.ctypes.data,
+                                       stats.ctypes.data_as(dp), reps, C.byref(us),
+                                       cyc.ctypes.data_as(dp) if cycles else None), ctx.h)
+    return L, X, stats, us.value, cyc
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("nb", [1, 2, 3, 7, 8, 9, 15, 16, 17, 31, 32, 33, 40, 47, 48, 49, 56, 57, 63, 64])
+def test_potrf_block_matches_lapack(tevo, nb, variant):
+    """The diagonal-block step of the CholeskyQR factorisation (csrc/cholqr.cu; the centre moves of orthogonalize!,
+    src/bondgate.jl:48): L = chol(G) and inv(L) of one nb x nb block, all three kernel variants, block sizes around
+    every 8-column panel boundary of the default kernel."""
+    rng = np.random.default_rng(100 * nb + variant)
+    B = _rand(rng, 2 * nb + 3, nb) * np.linspace(1.0, 6.0, nb)
+    G = B.conj().T @ B
+    G = (G + G.conj().T) / 2
+    L, X, stats, _, _ = _potrf_block(G, variant)
+    Lr = np.linalg.cholesky(G)
+    scale = np.abs(Lr).max()
+    assert np.abs(np.triu(L, 1)).max() == 0.0 and np.abs(np.triu(X, 1)).max() == 0.0
+    assert np.abs(np.diag(L).imag).max() == 0.0
+    assert np.abs(L - Lr).max() <= 1e-13 * scale * np.linalg.cond(Lr)
+    assert np.abs(L @ L.conj().T - G).max() <= 1e-14 * np.abs(G).max() * nb
+    assert np.abs(X @ Lr - np.eye(nb)).max() <= 1e-13 * np.linalg.cond(Lr)
+    d = np.diag(Lr).real
+    np.testing.assert_allclose(stats, [d.min(), d.max()], rtol=1e-12)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("where", [0, 5, 8, 37, 63])
+def test_potrf_block_flags_indefinite_block(tevo, where, variant):
+    """A non-positive pivot anywhere in the block sets stats[0] < 0 (the caller then takes the eigen-decomposition
+    route) instead of producing NaNs."""
+    rng = np.random.default_rng(7 + where)
+    B = _rand(rng, 140, 64)
+    G = B.conj().T @ B
+    G = (G + G.conj().T) / 2
+    G[where, where] = -1.0 if where == 0 else 0.5 * np.real(G[where, :where] @ np.linalg.solve(G[:where, :where], G[:where, where]))
+    L, X, stats, _, _ = _potrf_block(G, variant)
+    assert stats[0] < 0.0

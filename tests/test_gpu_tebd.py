@@ -54,6 +54,48 @@ def test_orthogonalize_preserves_state(tevo, oracle):
             assert np.abs(A @ A.conj().T - np.eye(A.shape[0])).max() < 1e-10
 
 
+@pytest.mark.parametrize("spread", [1.0, 30.0])
+@pytest.mark.parametrize("chi", [5, 37, 63, 64, 65, 100, 128, 130, 200])
+def test_centre_moves_across_cholesky_block_sizes(tevo, chi, spread):
+    """The centre moves factor a D x D Gram matrix in 64-wide diagonal blocks (csrc/cholqr.cu): bond dimensions below,
+    at and just above block boundaries.  Chain with d = 4 and bond dimensions 1, 2, 4, ..., chi, ..., 4, 2, 1 of generic
+    Gaussian tensors: every site matrix is at least 2:1 tall in the direction it is factored, so the moves stay well
+    conditioned (cond <= 10; the Gram route loses eps * cond^2) while the triangular factors are far from the
+    identity.  `spread` grades the chi bond by 1..spread, which pushes the pivot ratio of that move above the
+    single-pass threshold and exercises the second pass.  No oracle needed: exact isometry of every moved site and
+    the overlap with the untouched copy."""
+    rng = np.random.default_rng(1000 + chi)
+    k = int(np.ceil(np.log2(chi))) - 1
+    up = [2 ** i for i in range(k + 1)]
+    dims = up + [chi] + up[::-1]
+    N, d = len(dims) - 1, 4
+    A = []
+    for i in range(N):
+        a = rng.standard_normal((dims[i], d, dims[i + 1])) + 1j * rng.standard_normal((dims[i], d, dims[i + 1]))
+        A.append(a / np.linalg.norm(a) * np.sqrt(max(dims[i], dims[i + 1])))
+    mid = dims.index(chi)
+    w = np.linspace(1.0, spread, chi)
+    A[mid - 1] = A[mid - 1] * w
+    A[mid] = A[mid] / w[:, None, None]
+    p0 = tevo.MPS.from_tensors([np.asfortranarray(a) for a in A], llim=-1, rlim=N)
+    p = p0.copy()
+    nrm = tevo.inner(p0, p0).real
+    p.orthogonalize(N - 1)
+    ts = p.tensors()
+    assert [t.shape[2] for t in ts] == dims[1:]
+    for i in range(N - 1):
+        M = ts[i].reshape(-1, ts[i].shape[2])
+        assert np.abs(M.conj().T @ M - np.eye(M.shape[1])).max() < 1e-12, (i, M.shape)
+    assert abs(tevo.inner(p0, p) / nrm - 1.0) < 1e-12
+    p.orthogonalize(0)
+    ts = p.tensors()
+    for i in range(1, N):
+        M = ts[i].reshape(ts[i].shape[0], -1)
+        assert np.abs(M @ M.conj().T - np.eye(M.shape[0])).max() < 1e-12, (i, M.shape)
+    assert abs(tevo.inner(p0, p) / nrm - 1.0) < 1e-12
+    assert abs(tevo.inner(p, p).real / nrm - 1.0) < 1e-12
+
+
 @pytest.mark.parametrize("ortho", ["left", "right"])
 def test_apply_gate_matches_oracle(tevo, oracle, ortho):
     N = 8

@@ -103,6 +103,7 @@ PROTOTYPES = {
     "tevo_mps_set_lambda_from_device": (_I, [_P, _I, _I, _P]),
     "tevo_test_zgemm_time": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _DP]),
     "tevo_test_sbr": (_I, [_P, _I, _CP, _CP, _CP, _CP, _DP, _DP, _I, _DP, _CP]),
+    "tevo_test_potrf_block": (_I, [_P, _I, _I, _CP, _CP, _CP, _DP, _I, _DP, _DP]),
     "tevo_debug_set_heig_mode": (_I, [_I]),
     "tevo_debug_counters": (_I, [_P, _DP, _I]),
     "tevo_profile_enable": (_I, [_I]),

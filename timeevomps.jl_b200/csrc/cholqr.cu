@@ -147,6 +147,272 @@ __global__ void __launch_bounds__(256) potrf_block_reg_kernel(int nb, const cplx
   }
 }
 
+// Panel version of the same factorisation (default since round 2).  ncu on the register-tiled kernel above: 87 us per
+// block, 30-40 % of the warp samples at its 64 barriers, FP64 pipe 19 % busy.  Here the block is factored in 8 panels
+// of 8 columns, 2 barriers per panel:
+//   (b) warp 0 factors the panel in registers, lane l holding rows c0+l and c0+32+l; pivots and the multipliers of
+//       the 8 x 8 diagonal block travel by warp shuffles (a first version let every lane factor the diagonal block
+//       redundantly: one warp issues one FP64 instruction per ~4.8 cycles, measured, which made that phase 12 k
+//       cycles per panel);
+//   (c) the 136 4 x 4 tiles of the lower triangle are dealt to threads 0..135 column by column (tiles left of the
+//       current panel retire whole warps) and take the rank-8 update from a copy of the panel stored row-interleaved
+//       (sP[j][(i%4)*16 + i/4]) so that a warp's loads of 4 rows per thread are contiguous.
+// inv(L) follows by block rows (8 x 8 diagonal inverses in parallel, then X(bi, 0:bi) = -X(bi,bi) [L(bi, 0:bi)
+// X(0:bi, 0:bi)], 2 barriers per block row).  sL[c][i] = L(i,c), sX[c][i] = inv(L)(i,c): columns contiguous over rows.
+constexpr int PW = 8;        // panel width
+constexpr int LDX = NB + 1;  // sX row pitch: threads of a warp read 4 columns c at the same row k
+constexpr int NTILE = 136;   // 4 x 4 tiles of the lower triangle of a 64 x 64 block, diagonal included
+constexpr size_t POTRF_PANEL_SMEM = sizeof(cplx) * (NB * NB + NB * LDX + 2 * PW * NB) + sizeof(double) * NB;
+
+__device__ __forceinline__ void csubmulc(cplx& a, cplx x, cplx y) {  // a -= x * conj(y), four FMAs
+  a.x = fma(-x.x, y.x, a.x);
+  a.y = fma(-x.y, y.x, a.y);
+  a.x = fma(-x.y, y.y, a.x);
+  a.y = fma(x.x, y.y, a.y);
+}
+__device__ __forceinline__ void caddmul(cplx& a, cplx x, cplx y) {  // a += x * y, four FMAs
+  a.x = fma(x.x, y.x, a.x);
+  a.y = fma(x.x, y.y, a.y);
+  a.x = fma(-x.y, y.y, a.x);
+  a.y = fma(x.y, y.x, a.y);
+}
+__device__ __forceinline__ cplx shfl_c(cplx v, int src) {
+  return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+__global__ void __launch_bounds__(256) potrf_block_panel_kernel(int nb, const cplx* __restrict__ G,
+                                                                cplx* __restrict__ Lm, cplx* __restrict__ Xm, long ld,
+                                                                double* __restrict__ stats,
+                                                                long long* __restrict__ dbg) {
+  // dbg (tests only): thread 0's clock64 sums - [0] load, [1] publish + wait for the other warps' updates, [2] panel
+  // factor, [3] barrier after it, [4] own tile update, [5] L out + diagonal inverses, [6] inverse block rows, [7] total
+  long long tk0 = 0, tk = 0, acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define POTRF_MARK(slot)                \
+  if (dbg) { /* uniform: no divergence inside warp 0, whose shuffles would otherwise take their slow path */ \
+    const long long now_ = clock64();   \
+    acc[slot] += now_ - tk;             \
+    tk = now_;                          \
+  }
+  if (dbg) tk0 = tk = clock64();
+  extern __shared__ __align__(16) unsigned char smraw[];
+  cplx(*sL)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw);
+  cplx(*sX)[LDX] = reinterpret_cast<cplx(*)[LDX]>(smraw + sizeof(cplx) * NB * NB);
+  cplx(*sS)[NB] = reinterpret_cast<cplx(*)[NB]>(smraw + sizeof(cplx) * (NB * NB + NB * LDX));  // sS[m][c], m < 8
+  cplx(*sP)[NB] = sS + PW;                                                                     // interleaved panel
+  double* sinv = reinterpret_cast<double*>(smraw + sizeof(cplx) * (NB * NB + NB * LDX + 2 * PW * NB));
+  __shared__ int sfail;
+  __shared__ double spiv[2];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  // tile of this thread: column tj holds tiles ti = tj..15, columns laid one after the other
+  int ti = 0, tj = 0;
+  const bool tile = t < NTILE;
+  if (tile) {
+    int off = 0;
+    while (t >= off + 16 - tj) {
+      off += 16 - tj;
+      ++tj;
+    }
+    ti = tj + (t - off);
+  }
+  cplx a[4][4];
+  if (tile) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int i = 4 * ti + r, j = 4 * tj + c;
+        a[r][c] = (i < nb && j < nb) ? (i >= j ? G[(long)j * ld + i] : mk(0, 0)) : mk(i == j ? 1.0 : 0.0, 0.0);
+      }
+  }
+  if (t == 0) sfail = 0;
+  for (int e = t; e < NB * LDX; e += 256) (&sX[0][0])[e] = mk(0, 0);
+  for (int e = PW * ((nb + PW - 1) / PW) * NB + t; e < NB * NB; e += 256) (&sL[0][0])[e] = mk(0, 0);
+  POTRF_MARK(0)
+  double pmin = 1e300, pmax = 0.0;  // warp 0 only
+  const int npan = (nb + PW - 1) / PW;  // rows and columns >= nb are identity padding: whole panels of it are skipped
+  for (int p = 0; p < npan; ++p) {
+    const int c0 = PW * p;
+    // (a) the owners of the panel's two tile columns publish the current values (rows >= 4 tj)
+    if (tile && (tj >> 1) == p) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sL[4 * tj + c][4 * ti + r] = a[r][c];
+    }
+    __syncthreads();
+    POTRF_MARK(1)
+    // (b) factor the panel: warps 0..2, each with the 8 rows of the diagonal block in lanes 0..7 (redundantly, so that
+    // pivots and multipliers travel by warp shuffles) and 24 of the rows below it in lanes 8..31.  Entries above the
+    // diagonal (lane < c <= 7) are carried along as zeros.
+    {
+      const int rowbase = c0 + PW + 24 * warp;
+      if (warp < 3 && (warp == 0 || rowbase < NB)) {
+        POTRF_MARK(4)
+        const int irow = lane < PW ? c0 + lane : rowbase + (lane - PW);
+        const bool v = irow < NB;
+        cplx r[PW];
+#pragma unroll
+        for (int c = 0; c < PW; ++c) r[c] = (v && (lane >= PW || lane >= c)) ? sL[c0 + c][irow] : mk(0, 0);
+        bool bad = false;
+        POTRF_MARK(2)
+        // fully unrolled on purpose: a rolled version (current column always in r[0], the others rotating down) was
+        // measured slower (810 vs 550 cycles per column): its shuffles and FMAs serialise on the in-order issue
+#pragma unroll
+        for (int j = 0; j < PW; ++j) {
+          const double d = __shfl_sync(0xffffffffu, r[j].x, j);
+          if (!(d > 0.0) || !isfinite(d)) bad = true;  // uniform
+          const double inv = rsqrt(d), l = d * inv;
+          if (c0 + j < nb) {
+            pmin = fmin(pmin, l);
+            pmax = fmax(pmax, l);
+          }
+          r[j] = (lane > j) ? cscale(inv, r[j]) : (lane == j ? mk(l, 0.0) : mk(0, 0));
+          if (warp == 0 && lane == j) sinv[c0 + j] = inv;
+          cplx lc[PW];
+#pragma unroll
+          for (int c = j + 1; c < PW; ++c) lc[c] = shfl_c(r[j], c);  // L(c0+c, c0+j): all shuffles first
+#pragma unroll
+          for (int c = j + 1; c < PW; ++c) csubmulc(r[c], r[j], lc[c]);
+        }
+        if (!bad && v && (warp == 0 || lane >= PW)) {
+#pragma unroll
+          for (int c = 0; c < PW; ++c) {
+            const cplx val = (lane >= PW || lane >= c) ? r[c] : mk(0, 0);
+            sL[c0 + c][irow] = val;
+            sP[c][(irow & 3) * 16 + (irow >> 2)] = val;
+          }
+        }
+        POTRF_MARK(3)
+        if (bad && t == 0) sfail = 1;
+      }
+    }
+    POTRF_MARK(4)
+    __syncthreads();
+    if (sfail) {
+      if (t == 0) {
+        stats[0] = -1.0;
+        stats[1] = 0.0;
+      }
+      return;
+    }
+    // (c) rank-8 update of the lower tiles right of the panel
+    if (tile && (tj >> 1) > p) {
+#pragma unroll 2
+      for (int j = 0; j < PW; ++j) {
+        cplx li[4], lj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) li[r] = sP[j][r * 16 + ti];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) lj[c] = sP[j][c * 16 + tj];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) csubmulc(a[r][c], li[r], lj[c]);
+      }
+    }
+    // sP is rewritten only after the next barrier; sL columns of the next panel are disjoint from everything read here
+    POTRF_MARK(4)
+  }
+  if (t == 0) {
+    spiv[0] = pmin;
+    spiv[1] = pmax;
+  }
+  // L out (zeros above the diagonal)
+  for (int e = t; e < NB * NB; e += 256) {
+    const int i = e % NB, j = e / NB;
+    if (i < nb && j < nb) Lm[(long)j * ld + i] = (i >= j) ? sL[j][i] : mk(0, 0);
+  }
+  // inverse, diagonal 8 x 8 blocks: thread (w, cc) solves column cc of block w by forward substitution
+  if (t < PW * npan) {
+    const int w = t / PW, cc = t % PW, b0 = PW * w;
+    cplx x[PW];
+#pragma unroll
+    for (int i = 0; i < PW; ++i) {
+      cplx s = mk(0, 0);
+#pragma unroll
+      for (int k = 0; k < i; ++k) caddmul(s, sL[b0 + k][b0 + i], x[k]);
+      const double di = sinv[b0 + i];
+      x[i] = (i == cc) ? mk(di, 0.0) : (i > cc ? cscale(-di, s) : mk(0, 0));
+    }
+#pragma unroll
+    for (int i = 0; i < PW; ++i) sX[b0 + cc][b0 + i] = x[i];
+  }
+  __syncthreads();
+  POTRF_MARK(5)
+  // pairwise merging of diagonal ranges, inv([A 0; B C]) = [A^-1 0; -C^-1 (B A^-1), C^-1], block sizes h = 8, 16, 32:
+  // all pairs of a level together, 2 x 2 outputs per thread, the triangular structure of A^-1 and C^-1 in the loop
+  // bounds (everything above the diagonal of sX is zero).  A pair whose lower half is all padding is skipped; rows of
+  // padding inside a pair only ever produce rows of padding.
+  cplx* sT = &sS[0][0];  // 1024 entries: sS and sP, both free now
+  for (int h = PW; h < NB; h *= 2) {
+    const int hh = h / 2, tpp = hh * hh, ntile = (NB / (2 * h)) * tpp;
+    for (int e = t; e < ntile; e += 256) {  // T = B A^-1
+      const int pr = e / tpp, q = e % tpp, tr = q / hh, tc = q % hh;
+      const int lo = pr * 2 * h;
+      if (lo + h >= PW * npan) continue;
+      const int i0 = lo + h + 2 * tr, cc = lo + 2 * tc;
+      cplx s00 = mk(0, 0), s01 = mk(0, 0), s10 = mk(0, 0), s11 = mk(0, 0);
+      for (int m8 = (2 * tc) & ~7; m8 < h; m8 += 8) {  // whole chunks of 8 terms: A^-1 is zero above its diagonal
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int m = m8 + u;
+          const cplx b0 = sL[lo + m][i0], b1 = sL[lo + m][i0 + 1];
+          const cplx a0 = sX[cc][lo + m], a1 = sX[cc + 1][lo + m];
+          caddmul(s00, b0, a0);
+          caddmul(s01, b0, a1);
+          caddmul(s10, b1, a0);
+          caddmul(s11, b1, a1);
+        }
+      }
+      cplx* T = sT + pr * h * h + (2 * tr) * h + 2 * tc;
+      T[0] = s00;
+      T[1] = s01;
+      T[h] = s10;
+      T[h + 1] = s11;
+    }
+    __syncthreads();
+    for (int e = t; e < ntile; e += 256) {  // X(lower left) = -C^-1 T
+      const int pr = e / tpp, q = e % tpp, tr = q / hh, tc = q % hh;
+      const int lo = pr * 2 * h;
+      if (lo + h >= PW * npan) continue;
+      const int i0 = lo + h + 2 * tr, cc = lo + 2 * tc;
+      cplx s00 = mk(0, 0), s01 = mk(0, 0), s10 = mk(0, 0), s11 = mk(0, 0);
+      const cplx* T = sT + pr * h * h + 2 * tc;
+      for (int k8 = 0; k8 <= 2 * tr + 1; k8 += 8) {  // whole chunks: C^-1 is zero above its diagonal
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int k = k8 + u;
+          const cplx c0v = sX[lo + h + k][i0], c1v = sX[lo + h + k][i0 + 1];
+          const cplx t0 = T[k * h], t1 = T[k * h + 1];
+          caddmul(s00, c0v, t0);
+          caddmul(s01, c0v, t1);
+          caddmul(s10, c1v, t0);
+          caddmul(s11, c1v, t1);
+        }
+      }
+      sX[cc][i0] = mk(-s00.x, -s00.y);
+      sX[cc + 1][i0] = mk(-s01.x, -s01.y);
+      sX[cc][i0 + 1] = mk(-s10.x, -s10.y);
+      sX[cc + 1][i0 + 1] = mk(-s11.x, -s11.y);
+    }
+    __syncthreads();
+  }
+  POTRF_MARK(6)
+  for (int e = t; e < NB * NB; e += 256) {
+    const int i = e % NB, j = e / NB;
+    if (i < nb && j < nb) Xm[(long)j * ld + i] = (i >= j) ? sX[j][i] : mk(0, 0);
+  }
+  if (t == 0) {
+    stats[0] = spiv[0];
+    stats[1] = spiv[1];
+    if (dbg) {
+      acc[7] = clock64() - tk0;
+      for (int i = 0; i < 8; ++i) dbg[i] = acc[i];
+    }
+  }
+#undef POTRF_MARK
+}
+
 // E = G - I in place; stats[0] = max |E_ij| (non-negative doubles order like their bit patterns)
 __global__ void gram_minus_identity_kernel(int n, cplx* __restrict__ G, unsigned long long* __restrict__ maxbits) {
   double m = 0.0;
@@ -185,6 +451,19 @@ void CholQR::init() {
   TEVO_CUDA_CHECK(cudaMallocHost(&h_stats_, sizeof(double) * 2 * 128));
   TEVO_CUDA_CHECK(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(2 * sizeof(cplx) * NB * NB)));
+  TEVO_CUDA_CHECK(cudaFuncSetAttribute(potrf_block_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)POTRF_PANEL_SMEM));
+}
+
+void CholQR::block_step(cudaStream_t st, int variant, int nb, const cplx* G, cplx* L, cplx* X, long ld, double* stats,
+                        long long* cycles) {
+  if (variant == 0)
+    potrf_block_panel_kernel<<<1, 256, POTRF_PANEL_SMEM, st>>>(nb, G, L, X, ld, stats, cycles);
+  else if (variant == 2)
+    potrf_block_kernel<<<1, 1024, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G, L, X, ld, stats);
+  else
+    potrf_block_reg_kernel<<<1, 256, 0, st>>>(nb, G, L, X, ld, stats);
+  TEVO_LAUNCHED();
 }
 
 void CholQR::destroy() {
@@ -237,13 +516,9 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
     static const bool smem_version = getenv("TEVO_POTRF_SMEM") != nullptr;  // the 1024-thread shared-memory kernel
-    if (smem_version)
-      potrf_block_kernel<<<1, 1024, 2 * sizeof(cplx) * NB * NB, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j,
-                                                                       X + (long)j * n + j, n, d_stats_ + 2 * jb);
-    else
-      potrf_block_reg_kernel<<<1, 256, 0, st>>>(nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n,
-                                                d_stats_ + 2 * jb);
-    TEVO_LAUNCHED();
+    static const bool reg_version = getenv("TEVO_POTRF_REG") != nullptr;    // round 1's default (one barrier per column)
+    block_step(st, smem_version ? 2 : (reg_version ? 1 : 0), nb, G_ + (long)j * n + j, L + (long)j * n + j,
+               X + (long)j * n + j, n, d_stats_ + 2 * jb, nullptr);
     if (rest > 0) {
       // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H ; trailing: G(j+nb:, j+nb:) -= panel * panel^H
       zgemm(st, OP_N, OP_C, rest, nb, nb, ONE, G_ + (long)j * n + j + nb, n, X + (long)j * n + j, n, ZERO,

@@ -11,6 +11,11 @@ class CholQR {
   // A (m x n, ld m, m >= n) = Q (m x n, ld m) * C (n x n, ld n).  Returns false (outputs undefined) when A is too
   // ill-conditioned for the method; synchronises the stream twice (pivot checks).
   bool factor(cudaStream_t st, const cplx* A, int m, int n, cplx* Q, cplx* C);
+  // one diagonal-block step on device buffers (tests / timing): variant 0 = panel kernel (default), 1 = register-tiled,
+  // 2 = shared-memory kernel.  G, L, X: nb x nb column-major (ld), stats[2]; cycles: 8 clock64 phase sums of
+  // thread 0 (variant 0 only) or nullptr.
+  static void block_step(cudaStream_t st, int variant, int nb, const cplx* G, cplx* L, cplx* X, long ld, double* stats,
+                         long long* cycles);
 
  private:
   void ensure(int m, int n);
