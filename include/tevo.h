@@ -218,6 +218,9 @@ int tevo_test_sbr(tevo_ctx* ctx, int n, const tevo_complex* A, tevo_complex* ban
  * reps back-to-back launches; cycles_out (8 doubles or NULL): clock64 phase sums of variant 0 */
 int tevo_test_potrf_block(tevo_ctx* ctx, int variant, int nb, const tevo_complex* G, tevo_complex* L_out,
                           tevo_complex* X_out, double* stats_out, int reps, double* us_out, double* cycles_out);
+/* CTA tile of the DMMA ZGEMM (process-wide; tests): -1 = automatic by problem size (default), 0 = 128 x 64,
+ * 1 = 64 x 32, 2 = 32 x 32 (csrc/zgemm.cu, pick_tile) */
+int tevo_debug_set_zgemm_tile(int tile);
 /* Hermitian eigensolver variant used by the split (process-wide): 0 = default (one-stage blocked Householder
  * reduction; the two-stage one if the environment sets TEVO_HEIG_TWOSTAGE), 1 = one-stage, 2 = two-stage reduction
  * dense -> band of width 8 -> tridiagonal (n <= 2056; parity-tested, not yet faster: DESIGN.md) */

@@ -55,7 +55,7 @@ def test_orthogonalize_preserves_state(tevo, oracle):
 
 
 @pytest.mark.parametrize("spread", [1.0, 30.0])
-@pytest.mark.parametrize("chi", [5, 37, 63, 64, 65, 100, 128, 130, 200])
+@pytest.mark.parametrize("chi", [5, 37, 63, 64, 65, 100, 128, 130, 193, 200, 320, 449])
 def test_centre_moves_across_cholesky_block_sizes(tevo, chi, spread):
     """The centre moves factor a D x D Gram matrix in 64-wide diagonal blocks (csrc/cholqr.cu): bond dimensions below,
     at and just above block boundaries.  Chain with d = 4 and bond dimensions 1, 2, 4, ..., chi, ..., 4, 2, 1 of generic

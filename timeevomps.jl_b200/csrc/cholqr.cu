@@ -453,6 +453,9 @@ void CholQR::init() {
                                        (int)(2 * sizeof(cplx) * NB * NB)));
   TEVO_CUDA_CHECK(cudaFuncSetAttribute(potrf_block_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)POTRF_PANEL_SMEM));
+  TEVO_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&ev_diag_, &ev_inv_})
+    TEVO_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 }
 
 void CholQR::block_step(cudaStream_t st, int variant, int nb, const cplx* G, cplx* L, cplx* X, long ld, double* stats,
@@ -467,9 +470,22 @@ void CholQR::block_step(cudaStream_t st, int variant, int nb, const cplx* G, cpl
 }
 
 void CholQR::destroy() {
+  if (side_) {
+    cudaStreamSynchronize(side_);
+    cudaStreamDestroy(side_);
+    side_ = nullptr;
+  }
+  for (cudaEvent_t* e : {&ev_diag_, &ev_inv_})
+    if (*e) {
+      cudaEventDestroy(*e);
+      *e = nullptr;
+    }
   auto fr = [](void* p) {
     if (p) cudaFree(p);
   };
+  fr(part_);
+  part_ = nullptr;
+  part_cap_ = 0;
   fr(G_); fr(L1_); fr(L2_); fr(Linv_); fr(T_); fr(Q1_); fr(d_stats_);
   if (h_stats_) cudaFreeHost(h_stats_);
   G_ = L1_ = L2_ = Linv_ = T_ = Q1_ = nullptr;
@@ -500,25 +516,46 @@ void CholQR::ensure(int m, int n) {
   }
 }
 
-// one pass: Q = A L^-H with A^H A = L L^H; pivot extremes per diagonal block go to d_stats_
+// one pass: Q = A L^-H with A^H A = L L^H; pivot extremes per diagonal block go to d_stats_.
+//
+// The blocked Cholesky is a chain of nblk dependent steps (diagonal block by one CTA, panel GEMM, trailing update), each
+// far too small to fill the GPU.  The rows of inv(L) are therefore assembled beside the chain on a second stream
+// (side_): row b as soon as potrf(b) is done, X(b, 0:b) = -X_bb [L(b, 0:b) X(0:b, 0:b)] (split-K GEMM), so that only the
+// last block row remains after the chain: 0.62 -> 0.07 ms per pass at n = 1024 (gpurun_out -> profiles/r02_late_checks.log).
+// The pairwise merging used before ran entirely after the chain; TEVO_CHOL_PIPELINE=0 selects it again.  (Also tried:
+// splitting the trailing update into the next block column on the main stream and the rest on a third stream, so that
+// the next diagonal block starts earlier.  No gain: a step costs ~104 us either way, because each of its small GEMMs is
+// bound by its fixed launch + prologue cost, not by its flops.)
 void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q) {
   const cplx ONE = mk(1, 0), ZERO = mk(0, 0), MONE = mk(-1, 0);
   const int nblk = (n + NB - 1) / NB;
   cplx* X = Linv_;  // n x n: inverse of L, assembled below
+  static const bool pipeline = [] {
+    const char* e = getenv("TEVO_CHOL_PIPELINE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  const bool piped = pipeline && side_ && nblk >= 3;
   TEVO_CUDA_CHECK(cudaMemsetAsync(L, 0, sizeof(cplx) * (size_t)n * n, st));
   TEVO_CUDA_CHECK(cudaMemsetAsync(X, 0, sizeof(cplx) * (size_t)n * n, st));
   {
     ProfScope ps(st, P_CHOL_GRAM);
     zgemm_herm(st, OP_C, OP_N, n, m, ONE, A, m, A, m, ZERO, G_, n, false);  // Cholesky reads the lower part only
   }
+  static const bool smem_version = getenv("TEVO_POTRF_SMEM") != nullptr;  // the 1024-thread shared-memory kernel
+  static const bool reg_version = getenv("TEVO_POTRF_REG") != nullptr;    // round 1's default (one barrier per column)
+  const int variant = smem_version ? 2 : (reg_version ? 1 : 0);
   std::optional<ProfScope> pf;
   pf.emplace(st, P_CHOL_FACTOR);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j = jb * NB, nb = std::min(NB, n - j), rest = n - j - nb;
-    static const bool smem_version = getenv("TEVO_POTRF_SMEM") != nullptr;  // the 1024-thread shared-memory kernel
-    static const bool reg_version = getenv("TEVO_POTRF_REG") != nullptr;    // round 1's default (one barrier per column)
-    block_step(st, smem_version ? 2 : (reg_version ? 1 : 0), nb, G_ + (long)j * n + j, L + (long)j * n + j,
-               X + (long)j * n + j, n, d_stats_ + 2 * jb, nullptr);
+    block_step(st, variant, nb, G_ + (long)j * n + j, L + (long)j * n + j, X + (long)j * n + j, n, d_stats_ + 2 * jb,
+               nullptr);
+    if (piped && jb > 0) {  // block row jb of inv(L) (its rows of L were written by the panels of the steps before)
+      TEVO_CUDA_CHECK(cudaEventRecord(ev_diag_, st));
+      TEVO_CUDA_CHECK(cudaStreamWaitEvent(side_, ev_diag_, 0));
+      zgemm_splitk(side_, OP_N, OP_N, nb, j, j, ONE, L + j, n, X, n, ZERO, T_, nb, &part_, &part_cap_);
+      zgemm(side_, OP_N, OP_N, nb, j, nb, MONE, X + (long)j * n + j, n, T_, nb, ZERO, X + j, n);
+    }
     if (rest > 0) {
       // panel: L(j+nb:, j:j+nb) = G(j+nb:, j:j+nb) * inv(L_jj)^H ; trailing: G(j+nb:, j+nb:) -= panel * panel^H
       zgemm(st, OP_N, OP_C, rest, nb, nb, ONE, G_ + (long)j * n + j + nb, n, X + (long)j * n + j, n, ZERO,
@@ -528,42 +565,46 @@ void CholQR::pass(cudaStream_t st, const cplx* A, int m, int n, cplx* L, cplx* Q
     }
   }
   pf.reset();
-  std::optional<ProfScope> pi;
-  pi.emplace(st, P_CHOL_INV);
-  // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
-  // regular part: n = q * NB (+ tail); level s merges blocks [lo, lo+s) and [lo+s, lo+2s), all pairs of a level in
-  // two strided-batched GEMMs.  Irregular leftovers (n not a multiple of 2s) are merged one by one afterwards.
-  std::vector<int> bounds;
-  for (int b = 0; b < n; b += NB) bounds.push_back(b);
-  bounds.push_back(n);
-  while (bounds.size() > 2) {
-    std::vector<int> nbnd;
-    size_t k = 0;
-    // count leading pairs with identical sizes
-    const int s = bounds[1] - bounds[0];
-    int nreg = 0;
-    while (2 * (size_t)nreg + 2 < bounds.size() && bounds[2 * nreg + 1] - bounds[2 * nreg] == s &&
-           bounds[2 * nreg + 2] - bounds[2 * nreg + 1] == s)
-      ++nreg;
-    if (nreg > 0) {
-      const long bs = (long)2 * s * (n + 1);
-      // T_b = B_b * inv(A_b) ; X21_b = -inv(C_b) * T_b
-      zgemm_batched(st, OP_N, OP_N, s, s, s, ONE, L + s, n, bs, X, n, bs, ZERO, T_, s, (long)s * s, nreg);
-      zgemm_batched(st, OP_N, OP_N, s, s, s, MONE, X + (long)s * n + s, n, bs, T_, s, (long)s * s, ZERO, X + s, n, bs, nreg);
-      for (int q = 0; q < nreg; ++q) nbnd.push_back(bounds[2 * q]);
-      k = 2 * (size_t)nreg;
+  if (piped) {
+    ProfScope pi(st, P_CHOL_INV);  // what is left of the inverse after the chain: the join with the side stream
+    TEVO_CUDA_CHECK(cudaEventRecord(ev_inv_, side_));
+    TEVO_CUDA_CHECK(cudaStreamWaitEvent(st, ev_inv_, 0));
+  } else {
+    ProfScope pi(st, P_CHOL_INV);
+    // inverse of L by pairwise merging of diagonal ranges: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1]
+    // regular part: n = q * NB (+ tail); level s merges blocks [lo, lo+s) and [lo+s, lo+2s), all pairs of a level in
+    // two strided-batched GEMMs.  Irregular leftovers (n not a multiple of 2s) are merged one by one afterwards.
+    std::vector<int> bounds;
+    for (int b = 0; b < n; b += NB) bounds.push_back(b);
+    bounds.push_back(n);
+    while (bounds.size() > 2) {
+      std::vector<int> nbnd;
+      size_t k = 0;
+      // count leading pairs with identical sizes
+      const int s = bounds[1] - bounds[0];
+      int nreg = 0;
+      while (2 * (size_t)nreg + 2 < bounds.size() && bounds[2 * nreg + 1] - bounds[2 * nreg] == s &&
+             bounds[2 * nreg + 2] - bounds[2 * nreg + 1] == s)
+        ++nreg;
+      if (nreg > 0) {
+        const long bs = (long)2 * s * (n + 1);
+        // T_b = B_b * inv(A_b) ; X21_b = -inv(C_b) * T_b
+        zgemm_batched(st, OP_N, OP_N, s, s, s, ONE, L + s, n, bs, X, n, bs, ZERO, T_, s, (long)s * s, nreg);
+        zgemm_batched(st, OP_N, OP_N, s, s, s, MONE, X + (long)s * n + s, n, bs, T_, s, (long)s * s, ZERO, X + s, n, bs, nreg);
+        for (int q = 0; q < nreg; ++q) nbnd.push_back(bounds[2 * q]);
+        k = 2 * (size_t)nreg;
+      }
+      for (; k + 2 < bounds.size(); k += 2) {
+        const int lo = bounds[k], mid = bounds[k + 1], hi = bounds[k + 2];
+        const int s1 = mid - lo, s2 = hi - mid;
+        zgemm(st, OP_N, OP_N, s2, s1, s1, ONE, L + (long)lo * n + mid, n, X + (long)lo * n + lo, n, ZERO, T_, s2);
+        zgemm(st, OP_N, OP_N, s2, s1, s2, MONE, X + (long)mid * n + mid, n, T_, s2, ZERO, X + (long)lo * n + mid, n);
+        nbnd.push_back(lo);
+      }
+      for (; k < bounds.size(); ++k) nbnd.push_back(bounds[k]);
+      bounds = nbnd;
     }
-    for (; k + 2 < bounds.size(); k += 2) {
-      const int lo = bounds[k], mid = bounds[k + 1], hi = bounds[k + 2];
-      const int s1 = mid - lo, s2 = hi - mid;
-      zgemm(st, OP_N, OP_N, s2, s1, s1, ONE, L + (long)lo * n + mid, n, X + (long)lo * n + lo, n, ZERO, T_, s2);
-      zgemm(st, OP_N, OP_N, s2, s1, s2, MONE, X + (long)mid * n + mid, n, T_, s2, ZERO, X + (long)lo * n + mid, n);
-      nbnd.push_back(lo);
-    }
-    for (; k < bounds.size(); ++k) nbnd.push_back(bounds[k]);
-    bounds = nbnd;
   }
-  pi.reset();
   // Q = A * inv(L)^H
   ProfScope pq(st, P_CHOL_Q);
   zgemm(st, OP_N, OP_C, m, n, n, ONE, A, m, X, n, ZERO, Q, m);

@@ -23,6 +23,11 @@ class CholQR {
   cplx *G_ = nullptr, *L1_ = nullptr, *L2_ = nullptr, *Linv_ = nullptr, *T_ = nullptr, *Q1_ = nullptr;
   double *d_stats_ = nullptr, *h_stats_ = nullptr;
   double last_ratio_ = 0.0;
+  // side stream of the factorisation (pass()): the rows of inv(L) are assembled beside the Cholesky chain
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_diag_ = nullptr, ev_inv_ = nullptr;
+  cplx* part_ = nullptr;  // split-K partial sums of the inverse rows
+  size_t part_cap_ = 0;
  public:
   long n_single = 0, n_double = 0, n_fail = 0, n_series = 0;
   double ratio_hist[8] = {0};  // counts of pivot ratio in [1,2),[2,4),[4,8),[8,16),[16,64),[64,1e3),[1e3,1e6),fail

@@ -861,14 +861,15 @@ void Heig::factor(cudaStream_t st, int n, cplx* A, long lda) {
     TEVO_LAUNCHED();
   }
   // The compact-WY set-up below (T factors, V*T, pair factors: ~0.9 ms of small GEMMs at n = 2048) only needs the
-  // reflectors; the divide & conquer (~3.1 ms of latency-bound stages) only needs d and e, so they can run side by
-  // side (WY work on a second stream, joined by vectors()).  Measured: -3.8 % per sequential TEBD4 step at chi = 1024
-  // (profiles/r02_wy_overlap.log), all sequential tests green - but the layer-parallel mode (several lanes, each with
-  // its own pair of streams) hit an illegal memory access with it that is not understood yet, so it is OFF unless
-  // TEVO_WY_OVERLAP=1 and never used by the lanes.
+  // reflectors; the divide & conquer (~3.1 ms of latency-bound stages) only needs d and e, so they run side by side
+  // (WY work on a second stream, joined by vectors()).  Measured: -3.8 % per sequential TEBD4 step at chi = 1024
+  // (profiles/r02_wy_overlap.log), on by default since the end of round 2 for the single-lane configuration
+  // (max_ctas_ == 0: sequential TEBD, TDVP, centre moves).  The lanes of the layer-parallel mode never fork: their
+  // concurrency comes from the other lanes, and an early version that forked inside the lanes hit an illegal memory
+  // access that was not tracked down.  TEVO_WY_OVERLAP=0 switches the fork off.
   static const bool wy_overlap = [] {
     const char* e = getenv("TEVO_WY_OVERLAP");
-    return e ? atoi(e) != 0 : false;
+    return e ? atoi(e) != 0 : true;
   }();
   cudaStream_t main_st = st;
   if (wy_overlap && aux_ && max_ctas_ == 0 && n >= 256) {

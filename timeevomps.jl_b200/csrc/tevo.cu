@@ -1575,6 +1575,12 @@ extern "C" int tevo_test_potrf_block(tevo_ctx* ctx, int variant, int nb, const t
   TEVO_CATCH
 }
 
+extern "C" int tevo_debug_set_zgemm_tile(int tile) {
+  if (tile < -1 || tile > 2) return TEVO_EINVAL;
+  zgemm_force_tile(tile);
+  return TEVO_OK;
+}
+
 extern "C" int tevo_debug_set_heig_mode(int mode) {
   heig_set_mode(mode);
   return TEVO_OK;

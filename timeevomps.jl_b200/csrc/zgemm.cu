@@ -11,6 +11,7 @@
 // an m8n8k4 fragment, so no planar repack is required.  A complex MAC is 4 real DMMAs:
 //   Cre += Are*Bre ; Cre += (-Aim)*Bim ; Cim += Are*Bim ; Cim += Aim*Bre .
 // CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread).
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -117,7 +118,9 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
 // k-slice on the pipe the DMMAs use (SASS: the DADD/FSEL/DMUL of the inner loop disappear).
 // BULK: full interior tiles (and K a multiple of BK) are staged by the TMA engine (cp.async.bulk + mbarrier) instead
 // of one 16-byte cp.async per element; edge tiles keep the zero-filling cp.async path.
-template <bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB, bool BULK>
+// TBM x TBN: CTA tile (128 x 64 for problems that fill the GPU, 64 x 32 / 32 x 32 for small ones, see pick_tile): 8 warps
+// as 4 x 2, warp tile (TBM/4) x (TBN/2).
+template <int TBM, int TBN, bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB, bool BULK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
@@ -133,23 +136,24 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   A += A_KMAJOR ? (long)kb : (long)kb * lda;
   B += B_KMAJOR ? (long)kb : (long)kb * ldb;
   C += (long)zsplit * part_stride;
-  typedef Tile<BM, A_KMAJOR> TA;
-  typedef Tile<BN, B_KMAJOR> TB;
+  typedef Tile<TBM, A_KMAJOR> TA;
+  typedef Tile<TBN, B_KMAJOR> TB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* sA = reinterpret_cast<cplx*>(smem_raw);
   cplx* sB = sA + STAGES * TA::elems;
 
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  if (lower_only && n0 >= m0 + BM) return;  // Hermitian result: tiles strictly above the diagonal are mirrored later
+  constexpr int MI = TBM / 32, NJ = TBN / 16;  // 8 x 8 DMMA blocks per warp tile
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+  if (lower_only && n0 >= m0 + TBM) return;  // Hermitian result: tiles strictly above the diagonal are mirrored later
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int wm = (warp & 3) * (TBM / 4), wn = (warp >> 2) * (TBN / 2);
   const int g = lane >> 2, tq = lane & 3;
 
-  double cre[4][4][2], cim[4][4][2];
+  double cre[MI][NJ][2], cim[MI][NJ][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       cre[i][j][0] = cre[i][j][1] = 0.0;
       cim[i][j][0] = cim[i][j][1] = 0.0;
     }
@@ -158,10 +162,10 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   __shared__ unsigned long long full_bar[STAGES];
   // operands whose tile rows are long contiguous runs (m- / n-contiguous: 2 KB / 1 KB per k) go through the TMA
   // engine; k-contiguous operands (256-byte runs) stay on cp.async, where bulk copies measured slower
-  const bool interior = BULK && (m0 + BM <= M) && (n0 + BN <= N) && (K % BK == 0);
+  const bool interior = BULK && (m0 + TBM <= M) && (n0 + TBN <= N) && (K % BK == 0);
   const bool bulkA = interior && !A_KMAJOR, bulkB = interior && !B_KMAJOR;
   const bool bulk = bulkA || bulkB;
-  const unsigned stage_bytes = (unsigned)(((bulkA ? BM : 0) + (bulkB ? BN : 0)) * BK * sizeof(cplx));
+  const unsigned stage_bytes = (unsigned)(((bulkA ? TBM : 0) + (bulkB ? TBN : 0)) * BK * sizeof(cplx));
   if (bulk) {
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -176,11 +180,11 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       if (lane == 0) mbar_expect_tx(&full_bar[st], stage_bytes);
       __syncwarp();
-      if (bulkA) bulk_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, &full_bar[st], lane);
-      if (bulkB) bulk_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, &full_bar[st], lane);
+      if (bulkA) bulk_tile<TBM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, &full_bar[st], lane);
+      if (bulkB) bulk_tile<TBN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, &full_bar[st], lane);
     }
-    if (!bulkA) load_tile<BM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
-    if (!bulkB) load_tile<BN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
+    if (!bulkA) load_tile<TBM, A_KMAJOR>(sA + st * TA::elems, A, lda, m0, nx * BK, M, K);
+    if (!bulkB) load_tile<TBN, B_KMAJOR>(sB + st * TB::elems, B, ldb, n0, nx * BK, N, K);
   };
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -202,47 +206,47 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
     const cplx* b_s = sB + (kt % STAGES) * TB::elems;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double are[4], aim[4], nai[4], bre[4], bim[4];
+      double are[MI], aim[MI], nai[MI], bre[NJ], bim[NJ];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < MI; ++i) {
         cplx a = a_s[TA::idx(wm + i * 8 + g, kk + tq)];
         are[i] = a.x;
         aim[i] = (CONJA < 0) ? sa * a.y : (CONJA ? -a.y : a.y);
         nai[i] = -aim[i];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         cplx b = b_s[TB::idx(wn + j * 8 + g, kk + tq)];
         bre[j] = b.x;
         bim[j] = (CONJB < 0) ? sb * b.y : (CONJB ? -b.y : b.y);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+        for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+        for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], nai[i], bim[j]);
+        for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], nai[i], bim[j]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+        for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
     }
   }
   cp_async_wait<0>();
 
   const bool has_beta = (beta.x != 0.0 || beta.y != 0.0);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < MI; ++i) {
     const int row = m0 + wm + i * 8 + g;
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int col = n0 + wn + j * 8 + tq * 2 + e;
@@ -256,22 +260,22 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   }
 }
 
-template <bool AK, bool BK_, int CA, int CB, bool BULK>
+template <int TBM, int TBN, bool AK, bool BK_, int CA, int CB, bool BULK>
 void launch_cb(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
               long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
               long bsA, long bsB, long bsC, int lower_only) {
-  typedef Tile<BM, AK> TA;
-  typedef Tile<BN, BK_> TB;
+  typedef Tile<TBM, AK> TA;
+  typedef Tile<TBN, BK_> TB;
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
   static PerDeviceOnce once;
   once([&]() {
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<AK, BK_, CA, CB, BULK>,
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits * batch);
-  zgemm_dmma_kernel<AK, BK_, CA, CB, BULK><<<grid, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta,
-                                                                  C, ldc, splits > 1 ? Kc : K, part_stride, splits,
-                                                                  bsA, bsB, bsC, lower_only);
+  dim3 grid((M + TBM - 1) / TBM, (N + TBN - 1) / TBN, splits * batch);
+  zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK><<<grid, NTHREADS, smem, st>>>(
+      M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC,
+      lower_only);
   TEVO_LAUNCHED();
 }
 
@@ -284,16 +288,47 @@ int zgemm_bulk_default() {
   return v;
 }
 
+// CTA tile for a problem: one SM delivers 1/148 of the FP64 tensor throughput, so a GEMM with a handful of 128 x 64
+// tiles is bound by the time ONE SM needs for its tile (17 us at K = 64), however small the product is - the
+// panel / trailing GEMMs of the blocked Cholesky chain, everything at chi <= 256.  0: 128 x 64 (at least ~3/4 of a
+// wave of such tiles), 1: 64 x 32, 2: 32 x 32.  zgemm_force_tile(0|1|2) (tests; TEVO_ZGEMM_TILE at start-up) forces one.
+std::atomic<int> g_forced_tile{[] {
+  const char* e = getenv("TEVO_ZGEMM_TILE");
+  return e ? atoi(e) : -1;
+}()};
+int pick_tile(int M, int N, int zdim, int lower_only) {
+  const int forced = g_forced_tile.load(std::memory_order_relaxed);
+  if (forced >= 0 && forced <= 2) return forced;
+  auto tiles = [&](int bm, int bn) {
+    const long tm = (M + bm - 1) / bm, tn = (N + bn - 1) / bn;
+    long t = tm * tn;
+    if (lower_only) t = (t + tn) / 2;  // about half of the tiles touch the lower triangle
+    return t * zdim;
+  };
+  if (tiles(BM, BN) >= 111) return 0;
+  if (tiles(64, 32) >= 111) return 1;
+  return 2;
+}
+
 template <bool AK, bool BK_, int CA, int CB>
 void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
               long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
               long bsA, long bsB, long bsC, int lower_only) {
-  if (zgemm_bulk_default())
-    launch_cb<AK, BK_, CA, CB, true>(st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc,
-                                     part_stride, batch, bsA, bsB, bsC, lower_only);
-  else
-    launch_cb<AK, BK_, CA, CB, false>(st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc,
-                                      part_stride, batch, bsA, bsB, bsC, lower_only);
+#define TEVO_ZG_ARGS st, M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits, Kc, part_stride, batch, bsA, \
+                     bsB, bsC, lower_only
+  // the small tiles exist with compile-time conjugation signs and cp.async staging only (their operand rows are too
+  // short for the bulk copies to pay)
+  const int tile = (CA < 0) ? 0 : pick_tile(M, N, splits * batch, lower_only);
+  if (tile == 1) {
+    launch_cb<64, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
+  } else if (tile == 2) {
+    launch_cb<32, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
+  } else if (zgemm_bulk_default()) {
+    launch_cb<BM, BN, AK, BK_, CA, CB, true>(TEVO_ZG_ARGS);
+  } else {
+    launch_cb<BM, BN, AK, BK_, CA, CB, false>(TEVO_ZG_ARGS);
+  }
+#undef TEVO_ZG_ARGS
 }
 
 template <bool AK, bool BK_>
@@ -361,6 +396,7 @@ void launch_split(cudaStream_t st, int M, int N, int K, const cplx* A, long lda,
 
 long g_zgemm_launches = 0;
 std::atomic<long long> g_launches{0};
+void zgemm_force_tile(int tile) { g_forced_tile.store(tile); }
 
 void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
            long ldb, cplx beta, cplx* C, long ldc) {

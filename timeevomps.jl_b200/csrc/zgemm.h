@@ -12,4 +12,6 @@ void zgemm_herm(cudaStream_t st, Op ta, Op tb, int N, int K, cplx alpha, const c
 void zgemm_batched(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, long bsA,
                    const cplx* B, long ldb, long bsB, cplx beta, cplx* C, long ldc, long bsC, int batch);
 extern long g_zgemm_launches;
+// CTA tile selection (tests): -1 = automatic (by problem size), 0 = 128 x 64, 1 = 64 x 32, 2 = 32 x 32
+void zgemm_force_tile(int tile);
 }  // namespace tevo
