@@ -10,7 +10,8 @@
 // out of range) through a 3-stage shared-memory ring; one LDS.128 fetches the (re,im) pair a thread needs for
 // an m8n8k4 fragment, so no planar repack is required.  A complex MAC is 4 real DMMAs:
 //   Cre += Are*Bre ; Cre += (-Aim)*Bim ; Cim += Are*Bim ; Cim += Aim*Bre .
-// CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread).
+// CTA tile 128x64, 8 warps, warp tile 32x32 (16 DMMA blocks x re/im accumulators = 64 fp64 regs/thread); smaller
+// problems use 64x32 or 32x32 tiles of the same kernel (pick_tile below).
 #include <atomic>
 #include <cstdlib>
 #include <mutex>
@@ -288,10 +289,19 @@ int zgemm_bulk_default() {
   return v;
 }
 
-// CTA tile for a problem: one SM delivers 1/148 of the FP64 tensor throughput, so a GEMM with a handful of 128 x 64
-// tiles is bound by the time ONE SM needs for its tile (17 us at K = 64), however small the product is - the
-// panel / trailing GEMMs of the blocked Cholesky chain, everything at chi <= 256.  0: 128 x 64 (at least ~3/4 of a
-// wave of such tiles), 1: 64 x 32, 2: 32 x 32.  zgemm_force_tile(0|1|2) (tests; TEVO_ZGEMM_TILE at start-up) forces one.
+// CTA tile for a problem.  One SM delivers 1/148 of the FP64 tensor throughput, so a GEMM with a handful of 128 x 64
+// tiles is bound by the time ONE SM needs for its tile (17 us at K = 64), however small the product is - the panel /
+// trailing GEMMs of the blocked Cholesky chain, everything at chi <= 256.  And the smaller tiles are not slower per
+// flop where the big one has few waves: 2 - 3 CTAs per SM (116 / 80 registers, 92 / 61 KB of shared memory) hide the
+// DMMA and shared-memory latencies that 8 warps per SM cannot, and the last wave is fuller.  Measured on the B200
+// (tools/dev_zgemm.py with each tile forced, tools/dev_zgemm_tiles.py; profiles/r02_zgemm_tiles.json), TF/s for
+// 128x64 / 64x32 / 32x32:  theta NN 2048x2048x1024 28.1 / 31.3 / 30.2;  R = U^H theta CN 27.6 / 30.6 / 29.5;  rho
+// Hermitian NC 2048^2 x 2048 29.3 / 27.0 / 29.2;  rank-2k Hermitian 1920^2 x 128 16.4 / 19.6 / 21.9;  back-transformation
+// NN 2048x1024x128 20.9 / 25.3 / 24.3;  4096^3 32.5 / 31.9 / 31.1;  Cholesky panel NC 960x64x64 24.6 / 10.3 / 6.2 us;
+// chi = 256 theta NN 512x512x256 82 / 27 / 26 us.  Hence:
+//   Hermitian results (lower tiles only): 32 x 32 - the diagonal tiles waste the least;
+//   general results: 128 x 64 from 1024 such tiles on, else 64 x 32 if that gives a full wave at 2 CTAs per SM, else 32 x 32.
+// Returns 0: 128 x 64, 1: 64 x 32, 2: 32 x 32.  zgemm_force_tile(0|1|2) (tests; TEVO_ZGEMM_TILE at start-up) forces one.
 std::atomic<int> g_forced_tile{[] {
   const char* e = getenv("TEVO_ZGEMM_TILE");
   return e ? atoi(e) : -1;
@@ -299,14 +309,10 @@ std::atomic<int> g_forced_tile{[] {
 int pick_tile(int M, int N, int zdim, int lower_only) {
   const int forced = g_forced_tile.load(std::memory_order_relaxed);
   if (forced >= 0 && forced <= 2) return forced;
-  auto tiles = [&](int bm, int bn) {
-    const long tm = (M + bm - 1) / bm, tn = (N + bn - 1) / bn;
-    long t = tm * tn;
-    if (lower_only) t = (t + tn) / 2;  // about half of the tiles touch the lower triangle
-    return t * zdim;
-  };
-  if (tiles(BM, BN) >= 111) return 0;
-  if (tiles(64, 32) >= 111) return 1;
+  auto tiles = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * zdim; };
+  if (tiles(BM, BN) >= 1024) return 0;
+  if (lower_only) return 2;
+  if (tiles(64, 32) >= 296) return 1;
   return 2;
 }
 
