@@ -369,6 +369,24 @@ __device__ inline double secular_f(int K, const double* sdd, const double* sz2, 
   return 1.0 + rho * s;
 }
 
+// f and df/dmu in one pass (Newton steps of the root finder)
+__device__ inline void secular_fd(int K, const double* sdd, const double* sz2, double rho, double dorg, double mu,
+                                  int lane, double& f, double& fp) {
+  double s = 0.0, sp = 0.0;
+  for (int i = lane; i < K; i += 32) {
+    const double t = 1.0 / ((sdd[i] - dorg) - mu);
+    const double zt = sz2[i] * t;
+    s += zt;
+    sp = fma(zt, t, sp);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+  }
+  f = 1.0 + rho * s;
+  fp = rho * sp;
+}
+
 __global__ void __launch_bounds__(256)
 secular_kernel(const MergeDesc* __restrict__ descs, const int* __restrict__ Kin, const double* __restrict__ rho_in,
                const double* __restrict__ dd, const double* __restrict__ zz, int* __restrict__ org,
@@ -438,19 +456,47 @@ secular_kernel(const MergeDesc* __restrict__ descs, const int* __restrict__ Kin,
       x = xt;
     }
     double xhi = x;
-    for (int it = 0; it < 128; ++it) {
-      double xm;
-      if (xlo > 0.0 && xhi > 4.0 * xlo)
-        xm = sqrt(xlo) * sqrt(xhi);
+    // g(xlo) <= 0 < g(xhi) (xlo = 0: the pole at the origin).  Newton steps on g, safeguarded as in "rtsafe": a step
+    // that leaves the bracket, or that does not at least halve the previous one, is replaced by a bisection
+    // (geometric while the bracket spans more than a factor 4).  Plain bisection to the last bit (round 1) took ~60
+    // evaluations of the K-term sum per root; this takes ~8.
+    double xc = (xlo > 0.0) ? sqrt(xlo) * sqrt(xhi) : 0.5 * xhi;
+    double gv, gp;
+    secular_fd(K, sdd, sz2, rho, dorg, sg * xc, lane, gv, gp);
+    gv *= sg;  // dg/dx = f'(mu) > 0
+    double dxold = xhi - xlo, dx = dxold;
+    res = xc;
+    for (int it = 0; it < 120; ++it) {
+      if (gv == 0.0) {
+        res = xc;
+        break;
+      }
+      if (gv < 0.0)
+        xlo = xc;
       else
-        xm = 0.5 * (xlo + xhi);
-      if (!(xm > xlo) || !(xm < xhi)) break;
-      if (sg * secular_f(K, sdd, sz2, rho, dorg, sg * xm, lane) <= 0.0)
-        xlo = xm;
-      else
-        xhi = xm;
+        xhi = xc;
+      const double step = gv / gp;
+      const double cand = xc - step;
+      const bool newton_ok = (cand > xlo) && (cand < xhi) && (fabs(2.0 * gv) <= fabs(dxold * gp));
+      double xn;
+      dxold = dx;
+      if (newton_ok) {
+        dx = step;
+        xn = cand;
+      } else {
+        xn = (xlo > 0.0 && xhi > 4.0 * xlo) ? sqrt(xlo) * sqrt(xhi) : 0.5 * (xlo + xhi);
+        dx = xn - xc;
+      }
+      if (!(xn > xlo) || !(xn < xhi)) {  // no representable point left inside the bracket
+        res = 0.5 * (xlo + xhi);
+        break;
+      }
+      res = xn;
+      if (fabs(xn - xc) <= 2.0 * EPS * xn) break;  // converged to rounding
+      xc = xn;
+      secular_fd(K, sdd, sz2, rho, dorg, sg * xc, lane, gv, gp);
+      gv *= sg;
     }
-    res = 0.5 * (xlo + xhi);
   }
   if (lane == 0) {
     org[md.lo + j] = o;
