@@ -221,6 +221,9 @@ int tevo_test_potrf_block(tevo_ctx* ctx, int variant, int nb, const tevo_complex
 /* CTA tile of the DMMA ZGEMM (process-wide; tests): -1 = automatic by problem size (default), 0 = 128 x 64,
  * 1 = 64 x 32, 2 = 32 x 32 (csrc/zgemm.cu, pick_tile) */
 int tevo_debug_set_zgemm_tile(int tile);
+/* complex products of the 64 x 32 / 32 x 32 ZGEMM kernels (process-wide; tests): 1 = three real multiplications per
+ * complex one (default), 0 = four.  The Rayleigh-quotient GEMM of the split always uses four. */
+int tevo_debug_set_zgemm_3m(int on);
 /* Hermitian eigensolver variant used by the split (process-wide): 0 = default (one-stage blocked Householder
  * reduction; the two-stage one if the environment sets TEVO_HEIG_TWOSTAGE), 1 = one-stage, 2 = two-stage reduction
  * dense -> band of width 8 -> tridiagonal (n <= 2056; parity-tested, not yet faster: DESIGN.md) */

@@ -32,11 +32,12 @@ def zgemm_tile():
     """Forces one CTA tile of the DMMA ZGEMM for the duration of a test (the automatic choice depends on the problem
     size: small products would never reach the 128 x 64 kernel, large ones never the 32 x 32 one)."""
     from timeevomps_jl_b200._lib import load
-    yield lambda tile: load().tevo_debug_set_zgemm_tile(tile)
+    yield lambda tile, m3=1: load().tevo_debug_set_zgemm_tile(tile) + load().tevo_debug_set_zgemm_3m(m3)
     load().tevo_debug_set_zgemm_tile(-1)
+    load().tevo_debug_set_zgemm_3m(1)
 
 
-@pytest.mark.parametrize("tile", [-1, 0, 1, 2])
+@pytest.mark.parametrize("tile", [-1, 0, 1, 2, 11, 12])
 @pytest.mark.parametrize("ta", [0, 1, 2])
 @pytest.mark.parametrize("tb", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 4, 2), (7, 5, 3), (33, 65, 17), (128, 64, 16), (130, 70, 50),
@@ -44,9 +45,10 @@ def zgemm_tile():
 def test_zgemm_matches_numpy(tevo, zgemm_tile, ta, tb, shape, tile):
     """DMMA ZGEMM vs numpy complex128; tolerance 1e-13 relative to |A||B| (fp64 accumulation order differs).  Every
     shape with the automatic tile choice and with each of the three CTA tiles forced; the last two shapes reach the
-    64 x 32 and the 128 x 64 tile on their own."""
+    64 x 32 and the 128 x 64 tile on their own.  Tiles 11 / 12: the 64 x 32 / 32 x 32 kernels with four real
+    multiplications per complex product instead of their default three."""
     M, N, K = shape
-    assert zgemm_tile(tile) == 0
+    assert zgemm_tile(tile - 10 if tile >= 10 else tile, 0 if tile >= 10 else 1) == 0
     rng = np.random.default_rng(M * 1000 + N * 10 + K + ta * 3 + tb)
     A = _rand(rng, M, K) if ta == 0 else _rand(rng, K, M)
     B = _rand(rng, K, N) if tb == 0 else _rand(rng, N, K)

@@ -106,6 +106,7 @@ PROTOTYPES = {
     "tevo_test_potrf_block": (_I, [_P, _I, _I, _CP, _CP, _CP, _DP, _I, _DP, _DP]),
     "tevo_debug_set_heig_mode": (_I, [_I]),
     "tevo_debug_set_zgemm_tile": (_I, [_I]),
+    "tevo_debug_set_zgemm_3m": (_I, [_I]),
     "tevo_debug_counters": (_I, [_P, _DP, _I]),
     "tevo_profile_enable": (_I, [_I]),
     "tevo_profile_read": (_I, [C.c_char_p, C.c_size_t, _I]),

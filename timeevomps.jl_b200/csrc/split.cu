@@ -236,9 +236,13 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
   const int k1 = res.info.nkeep;
   DevBuf L1 = alloc((size_t)m * k1), R1 = alloc((size_t)k1 * n);
   double* lam2 = d_lam_;
+  // The rows of R = U^+ theta (columns of L = theta V) carry the refined Schmidt weights |R_i|^2 down to ~1e-9 of the
+  // largest one: this product keeps four real multiplications per complex one (ZgemmPrecise), every other GEMM of the
+  // path may use three (zgemm.cu)
   if (left) {
     heig_.vectors(st, d_perm_, k1, L1.p, m);
     ProfScope ps(st, P_SPLIT_GEMM);
+    ZgemmPrecise precise_rows;
     zgemm(st, OP_C, OP_N, k1, n, m, ONE, L1.p, m, theta, m, ZERO, R1.p, k1);
     rownorm2_kernel<<<(k1 + 127) / 128, 128, 0, st>>>(k1, n, R1.p, k1, lam2);
     TEVO_LAUNCHED();
@@ -246,6 +250,7 @@ SplitResult Split::run(cudaStream_t st, const cplx* theta, int m, int n, bool le
     cplx* V = ws(1, (size_t)n * k1);
     heig_.vectors(st, d_perm_, k1, V, n);
     ProfScope ps(st, P_SPLIT_GEMM);
+    ZgemmPrecise precise_cols;
     zgemm(st, OP_N, OP_N, m, k1, n, ONE, theta, m, V, n, ZERO, L1.p, m);
     conj_transpose(st, n, k1, V, n, R1.p, k1, true);
     colnorm2(st, L1.p, m, m, k1, lam2);

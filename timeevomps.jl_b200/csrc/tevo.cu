@@ -1581,6 +1581,11 @@ extern "C" int tevo_debug_set_zgemm_tile(int tile) {
   return TEVO_OK;
 }
 
+extern "C" int tevo_debug_set_zgemm_3m(int on) {
+  zgemm_set_3m(on != 0);
+  return TEVO_OK;
+}
+
 extern "C" int tevo_debug_set_heig_mode(int mode) {
   heig_set_mode(mode);
   return TEVO_OK;

@@ -121,8 +121,9 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
 // of one 16-byte cp.async per element; edge tiles keep the zero-filling cp.async path.
 // TBM x TBN: CTA tile (128 x 64 for problems that fill the GPU, 64 x 32 / 32 x 32 for small ones, see pick_tile): 8 warps
 // as 4 x 2, warp tile (TBM/4) x (TBN/2).
-template <int TBM, int TBN, bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB, bool BULK>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// M3: three real products per complex one (see the kernel body); small tiles only.
+template <int TBM, int TBN, bool A_KMAJOR, bool B_KMAJOR, int CONJA, int CONJB, bool BULK, bool M3>
+__global__ void __launch_bounds__(NTHREADS, (TBM == 128 ? 1 : (TBM == 64 ? 2 : 3)))
 zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ A, long lda, int conjA,
                   const cplx* __restrict__ B, long ldb, int conjB, cplx beta, cplx* __restrict__ C, long ldc, int Kc,
                   long part_stride, int nsplit, long bsA, long bsB, long bsC, int lower_only) {
@@ -150,13 +151,20 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   const int wm = (warp & 3) * (TBM / 4), wn = (warp >> 2) * (TBN / 2);
   const int g = lane >> 2, tq = lane & 3;
 
-  double cre[MI][NJ][2], cim[MI][NJ][2];
+  // 4M (default for the big tile): cre += Are Bre - Aim Bim, cim += Are Bim + Aim Bre - four DMMAs per complex MAC.
+  // 3M (M3): t1 = Are Bre, t2 = Aim Bim, t3 = (Are + Aim)(Bre + Bim); Re = t1 - t2, Im = t3 - t1 - t2 - three DMMAs and
+  // two FP64 adds per fragment.  The kernel is bound by DMMA issue (ncu: DMMA sub-pipe 85 % busy, math-pipe throttle
+  // the top stall), so the product count is what sets its time.  Error: normwise like 4M, eps |A||B| with a constant
+  // about twice as large for the imaginary part (Higham, "Stability of a method for multiplying complex matrices with
+  // three real matrix multiplications"); the three sums are combined once, after the k loop.
+  double cre[MI][NJ][2], cim[MI][NJ][2], ct3[M3 ? MI : 1][M3 ? NJ : 1][2];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       cre[i][j][0] = cre[i][j][1] = 0.0;
       cim[i][j][0] = cim[i][j][1] = 0.0;
+      if (M3) ct3[i][j][0] = ct3[i][j][1] = 0.0;
     }
 
   const int nk = (K + BK - 1) / BK;
@@ -221,22 +229,43 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
         bre[j] = b.x;
         bim[j] = (CONJB < 0) ? sb * b.y : (CONJB ? -b.y : b.y);
       }
+      if (M3) {
+        // cre <- t1, cim <- t2, ct3 <- t3
+        double asum[MI], bsum[NJ];
 #pragma unroll
-      for (int i = 0; i < MI; ++i)
+        for (int i = 0; i < MI; ++i) asum[i] = are[i] + aim[i];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+        for (int j = 0; j < NJ; ++j) bsum[j] = bre[j] + bim[j];
 #pragma unroll
-      for (int i = 0; i < MI; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+          for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
 #pragma unroll
-      for (int i = 0; i < MI; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], nai[i], bim[j]);
+          for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bim[j]);
 #pragma unroll
-      for (int i = 0; i < MI; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+          for (int j = 0; j < NJ; ++j) dmma(ct3[M3 ? i : 0][M3 ? j : 0][0], ct3[M3 ? i : 0][M3 ? j : 0][1], asum[i], bsum[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], are[i], bre[j]);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], are[i], bim[j]);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma(cre[i][j][0], cre[i][j][1], nai[i], bim[j]);
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma(cim[i][j][0], cim[i][j][1], aim[i], bre[j]);
+      }
     }
   }
   cp_async_wait<0>();
@@ -252,7 +281,9 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
       for (int e = 0; e < 2; ++e) {
         const int col = n0 + wn + j * 8 + tq * 2 + e;
         if (col >= N) continue;
-        cplx v = cmul(alpha, mk(cre[i][j][e], cim[i][j][e]));
+        const double pre = M3 ? cre[i][j][e] - cim[i][j][e] : cre[i][j][e];
+        const double pim = M3 ? (ct3[M3 ? i : 0][M3 ? j : 0][e] - cre[i][j][e]) - cim[i][j][e] : cim[i][j][e];
+        cplx v = cmul(alpha, mk(pre, pim));
         cplx* dst = C + (long)col * ldc + row;
         if (has_beta) v = cadd(v, cmul(beta, *dst));
         *dst = v;
@@ -261,7 +292,7 @@ zgemm_dmma_kernel(int M, int N, int Kfull, cplx alpha, const cplx* __restrict__ 
   }
 }
 
-template <int TBM, int TBN, bool AK, bool BK_, int CA, int CB, bool BULK>
+template <int TBM, int TBN, bool AK, bool BK_, int CA, int CB, bool BULK, bool M3 = false>
 void launch_cb(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, long lda, int conjA, const cplx* B,
               long ldb, int conjB, cplx beta, cplx* C, long ldc, int splits, int Kc, long part_stride, int batch,
               long bsA, long bsB, long bsC, int lower_only) {
@@ -270,11 +301,11 @@ void launch_cb(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, 
   const size_t smem = (size_t)STAGES * (TA::elems + TB::elems) * sizeof(cplx);
   static PerDeviceOnce once;
   once([&]() {
-    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK>,
+    TEVO_CUDA_CHECK(cudaFuncSetAttribute(zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK, M3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   });
   dim3 grid((M + TBM - 1) / TBM, (N + TBN - 1) / TBN, splits * batch);
-  zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK><<<grid, NTHREADS, smem, st>>>(
+  zgemm_dmma_kernel<TBM, TBN, AK, BK_, CA, CB, BULK, M3><<<grid, NTHREADS, smem, st>>>(
       M, N, K, alpha, A, lda, conjA, B, ldb, conjB, beta, C, ldc, splits > 1 ? Kc : K, part_stride, splits, bsA, bsB, bsC,
       lower_only);
   TEVO_LAUNCHED();
@@ -306,11 +337,21 @@ std::atomic<int> g_forced_tile{[] {
   const char* e = getenv("TEVO_ZGEMM_TILE");
   return e ? atoi(e) : -1;
 }()};
-int pick_tile(int M, int N, int zdim, int lower_only) {
+// three-multiplication complex products in the small-tile kernels: on by default (TEVO_ZGEMM_3M=0 / zgemm_set_3m(0):
+// four multiplications everywhere); a ZgemmPrecise scope on the calling thread forces four (the Rayleigh-quotient
+// GEMM of the split, whose small rows carry the relative accuracy of the small Schmidt weights)
+std::atomic<int> g_zgemm_3m{[] {
+  const char* e = getenv("TEVO_ZGEMM_3M");
+  return e ? atoi(e) : 1;
+}()};
+thread_local int tl_zgemm_precise = 0;
+int pick_tile(int M, int N, int zdim, int lower_only, bool m3) {
   const int forced = g_forced_tile.load(std::memory_order_relaxed);
   if (forced >= 0 && forced <= 2) return forced;
   auto tiles = [&](int bm, int bn) { return (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * zdim; };
-  if (tiles(BM, BN) >= 1024) return 0;
+  // with three multiplications per product the small tiles win at every size (theta shape 36.6 TF/s against 32.4 for
+  // the 128 x 64 kernel at 4096^3); the big tile is for four-multiplication products of at least 1024 tiles
+  if (!m3 && tiles(BM, BN) >= 1024) return 0;
   if (lower_only) return 2;
   if (tiles(64, 32) >= 296) return 1;
   return 2;
@@ -324,11 +365,18 @@ void launch_c(cudaStream_t st, int M, int N, int K, cplx alpha, const cplx* A, l
                      bsB, bsC, lower_only
   // the small tiles exist with compile-time conjugation signs and cp.async staging only (their operand rows are too
   // short for the bulk copies to pay)
-  const int tile = (CA < 0) ? 0 : pick_tile(M, N, splits * batch, lower_only);
+  const bool m3 = g_zgemm_3m.load(std::memory_order_relaxed) != 0 && tl_zgemm_precise == 0;
+  const int tile = (CA < 0) ? 0 : pick_tile(M, N, splits * batch, lower_only, m3);
   if (tile == 1) {
-    launch_cb<64, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
+    if (m3)
+      launch_cb<64, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false, true>(TEVO_ZG_ARGS);
+    else
+      launch_cb<64, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
   } else if (tile == 2) {
-    launch_cb<32, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
+    if (m3)
+      launch_cb<32, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false, true>(TEVO_ZG_ARGS);
+    else
+      launch_cb<32, 32, AK, BK_, CA < 0 ? 0 : CA, CB < 0 ? 0 : CB, false>(TEVO_ZG_ARGS);
   } else if (zgemm_bulk_default()) {
     launch_cb<BM, BN, AK, BK_, CA, CB, true>(TEVO_ZG_ARGS);
   } else {
@@ -403,6 +451,9 @@ void launch_split(cudaStream_t st, int M, int N, int K, const cplx* A, long lda,
 long g_zgemm_launches = 0;
 std::atomic<long long> g_launches{0};
 void zgemm_force_tile(int tile) { g_forced_tile.store(tile); }
+void zgemm_set_3m(int on) { g_zgemm_3m.store(on); }
+ZgemmPrecise::ZgemmPrecise() { ++tl_zgemm_precise; }
+ZgemmPrecise::~ZgemmPrecise() { --tl_zgemm_precise; }
 
 void zgemm(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alpha, const cplx* A, long lda, const cplx* B,
            long ldb, cplx beta, cplx* C, long ldc) {

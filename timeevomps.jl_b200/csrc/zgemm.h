@@ -14,4 +14,11 @@ void zgemm_batched(cudaStream_t st, Op ta, Op tb, int M, int N, int K, cplx alph
 extern long g_zgemm_launches;
 // CTA tile selection (tests): -1 = automatic (by problem size), 0 = 128 x 64, 1 = 64 x 32, 2 = 32 x 32
 void zgemm_force_tile(int tile);
+// three-multiplication complex products in the small-tile kernels (default on); 0 = four multiplications everywhere
+void zgemm_set_3m(int on);
+// while alive on a thread, that thread's products use four multiplications
+struct ZgemmPrecise {
+  ZgemmPrecise();
+  ~ZgemmPrecise();
+};
 }  // namespace tevo
