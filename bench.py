@@ -263,8 +263,9 @@ def panel_roofline(prof, c0, c1, hbm_peak, peak_src, label="tridiag_panel_kernel
             "algorithmic_bytes_per_launch": bytes_alg / max(nlaunch, 1), "launches": nlaunch,
             "factorisations": nfact, "avg_launch_ms": tk["ms"] / max(tk["count"], 1),
             "share_of_step": tk["ms"] / total_prof,
-            "limiter": "latency, not bandwidth: every column of the Householder tridiagonalisation is a chain of two "
-                       "grid-wide barriers and dependent L2 round trips; the trailing matrix stays L2-resident inside a "
+            "limiter": "latency and L2 traffic, not HBM bandwidth: every column of the Householder tridiagonalisation is a "
+                       "chain of two grid-wide barriers and dependent L2 round trips (72 % of its time at n = 2048), and "
+                       "the matrix-vector product runs at ~60 % of the L2 throughput cap; the trailing matrix stays L2-resident inside a "
                        "launch, so DRAM sees it about once per 64 columns (traffic) while the matrix-vector products "
                        "read it once per column (algorithmic bytes).  The HBM roof is the contract's denominator; the "
                        "kernel cannot reach it by construction of the one-stage algorithm"}
@@ -539,6 +540,8 @@ def run_tdvp(args):
             "roofline": {"kernel": "zgemm_dmma_kernel (H_eff legs) + mid_contract_kernel", "bound": "tensor",
                          "achieved": ach, "peak": zpeak, "unit": "TFLOP/s", "frac": (ach / zpeak) if ach else None,
                          "traffic": None, "peak_source": "measured cuBLAS ZGEMM 4096^3 (profiles/r01_fp64_peaks.json)",
+                         "note": "effective rate in the 8*M*N*K convention: the 64x32 / 32x32 ZGEMM kernels form a "
+                                 "complex product from three real multiplications (csrc/zgemm.cu), cuBLAS ZGEMM from four",
                          "share_of_step": hk["ms"] / (sum(v["ms"] for v in prof.values()) or 1.0)},
             "phases_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
     emit(line)
