@@ -6,7 +6,8 @@
 
 namespace tevo {
 
-// experimental cluster-resident tail of the tridiagonalisation (tail.cu; enabled by TEVO_CLUSTER_TAIL=<cluster size>)
+// cluster-resident tail of the tridiagonalisation (tail.cu; on by default with a 16-CTA cluster in the single-lane
+// configuration, TEVO_CLUSTER_TAIL=<0 | cluster size>)
 int tridiag_tail_max_m(int cluster);
 void tridiag_tail(cudaStream_t st, int cluster, int n, int t0, cplx* A, long lda, double* d, double* e, cplx* taus);
 

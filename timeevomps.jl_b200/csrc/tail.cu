@@ -1,5 +1,6 @@
-// EXPERIMENTAL (off unless TEVO_CLUSTER_TAIL is set; not yet validated on hardware - see DESIGN.md section 9):
-// the last columns of the Householder tridiagonalisation inside ONE thread-block cluster.
+// The last columns of the Householder tridiagonalisation inside ONE thread-block cluster (default since round 2 in
+// the single-lane configuration, 16-CTA cluster; validated on the B200 at cluster sizes 1 / 8 / 16 and measured at
+// -5 % / -14 % of the panel time at n = 2048 / 1024: profiles/r02_deferred_checks.log; TEVO_CLUSTER_TAIL=0 disables it).
 //
 // The cooperative panel kernel (heig.cu) pays ~8 us per column for two grid barriers and the dependent L2 round
 // trips between them, whatever the size of the trailing matrix.  Once the trailing matrix fits the shared memory of

@@ -113,9 +113,9 @@ __device__ inline void load_tile(cplx* s, const cplx* __restrict__ g, long ld, i
   }
 }
 
-// CONJA / CONJB: -1 = sign taken from the run-time arguments conjA / conjB (default, the validated path);
-// 0 / 1 = compile-time (EXPERIMENTAL, TEVO_ZGEMM_CTSIGN=1, not yet run on hardware): the signs of the imaginary
-// parts then fold into the operand-negation modifiers of DMMA instead of costing 12 FP64 multiplies/negations per
+// CONJA / CONJB: 0 / 1 = compile-time conjugation (default since round 2: +4.6 % at the theta shape, tests green on the
+// B200, profiles/r02_checks.log); -1 = sign taken from the run-time arguments conjA / conjB (TEVO_ZGEMM_CTSIGN=0, 128 x 64
+// tile only).  With compile-time signs the signs of the imaginary parts fold into the operand-negation modifiers of DMMA instead of costing 12 FP64 multiplies/negations per
 // k-slice on the pipe the DMMAs use (SASS: the DADD/FSEL/DMUL of the inner loop disappear).
 // BULK: full interior tiles (and K a multiple of BK) are staged by the TMA engine (cp.async.bulk + mbarrier) instead
 // of one 16-byte cp.async per element; edge tiles keep the zero-filling cp.async path.
